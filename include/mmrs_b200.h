@@ -1,0 +1,189 @@
+/*
+ * mmrs_b200.h -- C ABI of the B200-native retrieval hot path.
+ *
+ * The reference (chy980959830/Multi-Modal-Retrieval-System-Image-Search-and-Data-Governance)
+ * is pure Python and has no FFI of its own: its "operator
+ * interface" for this path is a handful of module-level Python functions.  This
+ * header is therefore the boundary a replacement library must export so that the
+ * Python mirror of those functions (the package next to this directory) can
+ * bind it with ctypes.  Each entry point names the reference expression it
+ * replaces (paths relative to the reference checkout):
+ *
+ *   mmrs_full_scores      code/search_image.py:107   `100. * features.cuda() @ ref_feature.t()`
+ *                         CLIP/lab3.py:113-114, CLIP-Chinese/lab_chinese.py:116-117,
+ *                         CLIP/union_dataset.py:255-256 (per-class GEMVs, one call)
+ *   mmrs_search_topk      code/search_image.py:107 + code/utils.py:17
+ *                         `output.topk(k, 1, True, True)` fused, score matrix never stored
+ *   mmrs_topk_merge       (new) merge of per-shard top-k after the all-gather
+ *   mmrs_selfjoin_pairs   tool/find_repeated_in_same_folder.py:76-95 /
+ *                         tool/delete repeated.py:127-135 (pairwise join loop), with the
+ *                         predicate cos(e_i, e_j) >= tau named by BASELINE.json
+ *   mmrs_threshold_sweep  code/search_image.py:39-79 (eval_threshold / find_thresholds)
+ *
+ * Conventions
+ *   - every function returns an int status: 0 = ok, negative = error (table below);
+ *     nothing throws across the ABI.  mmrs_last_error() returns a thread-local
+ *     NUL-terminated description of the most recent failure on the calling thread.
+ *   - pointers named d_* are caller-owned DEVICE pointers, h_* are HOST pointers.
+ *     The library allocates no persistent device memory: scratch space is a
+ *     caller-provided workspace whose size comes from the matching
+ *     *_workspace_bytes() query.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *     Calls are re-entrant; there is no global mutable state besides the
+ *     thread-local error string and a per-thread pinned status word.
+ *   - matrices are row-major; `ld_*` is the row stride in ELEMENTS.
+ *   - there is no CPU fallback: on a device that is not compute capability 10.x
+ *     every compute entry point returns MMRS_ERR_ARCH.
+ */
+#ifndef MMRS_B200_H_
+#define MMRS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library itself is built with -fvisibility=hidden */
+#endif
+
+#define MMRS_ABI_VERSION 1
+
+/* status codes */
+#define MMRS_OK 0
+#define MMRS_ERR_ARG (-1)        /* bad argument (shape, alignment, k > n_rows, ...)   */
+#define MMRS_ERR_CUDA (-2)       /* a CUDA runtime / driver call failed               */
+#define MMRS_ERR_ARCH (-3)       /* device is not sm_100 (B200)                        */
+#define MMRS_ERR_WORKSPACE (-4)  /* workspace too small or misaligned                  */
+#define MMRS_ERR_ZERO_NORM (-5)  /* normalize_queries=1 and a query row has zero norm
+                                    (the reference yields NaN here, search_image.py:157
+                                    has no epsilon; we refuse instead)                 */
+#define MMRS_ERR_CAPACITY (-6)   /* output capacity too small (self-join pair buffer);
+                                    the required count is still reported             */
+#define MMRS_ERR_INTERNAL (-7)
+
+/* element types of the gallery / embedding matrix */
+#define MMRS_DTYPE_F32 0
+#define MMRS_DTYPE_BF16 1
+
+/* kernel selection for mmrs_search_topk / mmrs_full_scores */
+#define MMRS_PATH_AUTO 0   /* K1 for small batches, K2 (tcgen05) otherwise               */
+#define MMRS_PATH_GEMV 1   /* K1: 128-bit streaming + warp-shuffle dot products            */
+#define MMRS_PATH_MMA 2    /* K2: TMA + tcgen05.mma, bf16 gallery only                      */
+
+int mmrs_abi_version(void);
+const char* mmrs_last_error(void);
+
+/* 0 when `device` is a compute-capability-10.x GPU, MMRS_ERR_ARCH / MMRS_ERR_CUDA otherwise. */
+int mmrs_device_check(int device);
+
+/* ---- search: scores ------------------------------------------------------------------- */
+
+/* Scratch bytes needed by mmrs_full_scores. */
+size_t mmrs_full_scores_workspace_bytes(int64_t n_rows, int32_t dim, int32_t gallery_dtype,
+                                        int32_t n_queries);
+
+/*
+ * out[q, i] = scale * <q_q, g_i>     (q_q first divided by its L2 norm when normalize_queries)
+ * d_out_scores is [n_queries, ld_out] fp32, ld_out >= n_rows.
+ * Replaces code/search_image.py:107 (n_queries == 1, scale == 100, normalize_queries == 0).
+ */
+int mmrs_full_scores(const void* d_gallery, int64_t n_rows, int32_t dim, int64_t ld_gallery,
+                     int32_t gallery_dtype, const float* d_queries, int32_t n_queries,
+                     int64_t ld_queries, int32_t normalize_queries, float scale, int32_t path,
+                     float* d_out_scores, int64_t ld_out, void* d_workspace,
+                     size_t workspace_bytes, void* stream);
+
+/* ---- search: fused top-k ------------------------------------------------------------- */
+
+size_t mmrs_search_workspace_bytes(int64_t n_rows, int32_t dim, int32_t gallery_dtype,
+                                   int32_t n_queries, int32_t k);
+
+/*
+ * Per-query top-k of scale * <q, g_i> over the rows of one gallery shard, returned like
+ * torch.topk(k, dim=1, largest=True, sorted=True) (code/utils.py:17): values [n_queries, k]
+ * fp32 descending, indices [n_queries, k] int64.  Equal scores are ordered by ascending
+ * row index.  index_offset is added to every index (the shard's first global row).
+ * gallery_dtype BF16: the query is rounded to bf16 after normalisation (tensor-core mode);
+ * F32: everything is fp32.
+ * The call synchronises `stream` before returning (it must read back a status word).
+ */
+int mmrs_search_topk(const void* d_gallery, int64_t n_rows, int32_t dim, int64_t ld_gallery,
+                     int32_t gallery_dtype, const float* d_queries, int32_t n_queries,
+                     int64_t ld_queries, int32_t k, int32_t normalize_queries, float scale,
+                     int64_t index_offset, int32_t path, float* d_out_values,
+                     int64_t* d_out_indices, void* d_workspace, size_t workspace_bytes,
+                     void* stream);
+
+/*
+ * Same, but the queries come from and the results go to HOST memory (pinned memory makes
+ * the copies asynchronous); the gallery stays device-resident.  This is the call shape of
+ * the reference's get_similarity(): host tensors in, host numpy out
+ * (code/search_image.py:105-109), minus the per-call upload of the whole gallery.
+ * The workspace must be mmrs_search_workspace_bytes() + mmrs_search_host_staging_bytes().
+ */
+size_t mmrs_search_host_staging_bytes(int32_t dim, int32_t n_queries, int32_t k);
+int mmrs_search_topk_host(const void* d_gallery, int64_t n_rows, int32_t dim, int64_t ld_gallery,
+                          int32_t gallery_dtype, const float* h_queries, int32_t n_queries,
+                          int64_t ld_queries, int32_t k, int32_t normalize_queries, float scale,
+                          int64_t index_offset, int32_t path, float* h_out_values,
+                          int64_t* h_out_indices, void* d_workspace, size_t workspace_bytes,
+                          void* stream);
+
+/* ---- multi-GPU merge -------------------------------------------------------------------- */
+
+size_t mmrs_topk_merge_workspace_bytes(int32_t n_lists, int32_t n_queries, int32_t k_in);
+
+/*
+ * Merge n_lists per-shard results (as gathered by an all-gather: values [n_lists, n_queries,
+ * k_in] fp32, indices [n_lists, n_queries, k_in] int64 GLOBAL row ids < 2^32) into the global
+ * top-k_out per query with the same order rule (score desc, index asc).
+ */
+int mmrs_topk_merge(const float* d_values_in, const int64_t* d_indices_in, int32_t n_lists,
+                    int32_t n_queries, int32_t k_in, int32_t k_out, float* d_out_values,
+                    int64_t* d_out_indices, void* d_workspace, size_t workspace_bytes,
+                    void* stream);
+
+/* ---- near-duplicate self-join ---------------------------------------------------------- */
+
+size_t mmrs_selfjoin_workspace_bytes(int64_t n_rows, int32_t dim, int32_t dtype);
+
+/*
+ * All pairs (i, j), i < j, row_begin <= i < row_end, with <e_i, e_j> >= threshold, where the
+ * rows of d_emb [n_rows, dim] are fp32 (exact mode).  Pairs are written as int64 [count, 2]
+ * in UNSPECIFIED order (the Python tier sorts them lexicographically); *d_out_count (device
+ * int64) receives the number found even when it exceeds `capacity`
+ * (then MMRS_ERR_CAPACITY is returned and only `capacity` pairs are valid).
+ * [row_begin, row_end) is this rank's slice of the upper-triangular schedule.
+ * The call synchronises `stream`.
+ */
+int mmrs_selfjoin_pairs(const void* d_emb, int64_t n_rows, int32_t dim, int64_t ld_emb,
+                        int32_t dtype, float threshold, int64_t row_begin, int64_t row_end,
+                        int64_t* d_out_pairs, int64_t capacity, int64_t* d_out_count,
+                        void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* ---- threshold / F1 sweep (the reference's consumer of the scores) ------------------ */
+
+/*
+ * For each of n_thresholds thresholds t: tp = #{pos >= t}, fp = #{neg >= t} over fp32 device
+ * score vectors.  d_out_counts is int64 [n_thresholds, 2] = (tp, fp).
+ * Replaces the O(T*N) Python `sum(pos_res >= threshold)` loops of
+ * code/search_image.py:43-45 inside find_thresholds (:69-70).  Thresholds must be ASCENDING
+ * (np.linspace(min, max, 200) is) and n_thresholds <= 4096; they are fp64 like the
+ * np.linspace grid of :61; the comparison is done in fp64 as numpy does (fp32 array vs
+ * python float promotes the array).
+ */
+size_t mmrs_threshold_sweep_workspace_bytes(int32_t n_thresholds);
+int mmrs_threshold_sweep(const float* d_pos, int64_t n_pos, const float* d_neg, int64_t n_neg,
+                         const double* d_thresholds, int32_t n_thresholds,
+                         int64_t* d_out_counts, void* d_workspace, size_t workspace_bytes,
+                         void* stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMRS_B200_H_ */

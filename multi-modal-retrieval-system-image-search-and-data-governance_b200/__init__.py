@@ -1,0 +1,30 @@
+"""B200-native retrieval hot path of
+chy980959830/Multi-Modal-Retrieval-System-Image-Search-and-Data-Governance.
+
+Import as `mmrs_b200` (see ../mmrs_b200.py).  The public names mirror the reference's module-level
+functions for this path (same names, positional order and return tuples):
+
+    code/search_image.py   get_similarity, construct_dataset, eval_threshold, find_thresholds
+    tool/find_repeated.py  get_all_images, find_and_remove_duplicate_images
+    tool/find_repeated_in_same_folder.py
+                           find_and_remove_duplicate_images (same-folder form)
+
+plus the tensor-level entry points they sit on: search_topk, full_scores, find_duplicate_pairs,
+DeviceGallery, ShardedGallery.  Everything computes through the C-ABI CUDA library
+(include/mmrs_b200.h); there is no CPU path -- without a B200 the calls raise.
+"""
+from . import _cabi  # noqa: F401  (fails loudly when the CUDA library is missing)
+from .gallery import DeviceGallery, load_feature_cache
+from .search import (construct_dataset, eval_threshold, find_thresholds, full_scores,
+                     get_similarity, search_topk, threshold_sweep_counts)
+from .dedup import (find_and_remove_duplicate_images, find_duplicate_pairs,
+                    find_and_remove_near_duplicate_images, get_all_images, greedy_first_keeper)
+from .sharded import ShardedGallery, shard_bounds
+
+__all__ = [
+    "DeviceGallery", "ShardedGallery", "construct_dataset", "eval_threshold", "find_thresholds",
+    "find_and_remove_duplicate_images", "find_and_remove_near_duplicate_images",
+    "find_duplicate_pairs", "full_scores", "get_all_images", "get_similarity",
+    "greedy_first_keeper", "load_feature_cache", "search_topk", "shard_bounds",
+    "threshold_sweep_counts",
+]

@@ -1,0 +1,577 @@
+// api.cu -- the extern "C" boundary declared in include/mmrs_b200.h and the host-side
+// orchestration of a search: query preparation, the phase schedule of plan.h, kernel choice
+// (K1 streaming GEMV for small batches, K2 tcgen05 for the rest), the status read-back and the
+// exhaustive re-run of a query whose candidate list overflowed.
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "plan.h"
+
+namespace mmrs {
+
+// implemented in selfjoin.cu / scan_mma.cu
+cudaError_t launch_selfjoin_f32(const float* emb, int64_t n_rows, int32_t dim, int64_t ld,
+                                float threshold, int64_t row_begin, int64_t row_end,
+                                int64_t* out_pairs, int64_t capacity, int64_t* out_count,
+                                int sm_count, cudaStream_t stream);
+cudaError_t launch_threshold_sweep(const float* pos, int64_t n_pos, const float* neg, int64_t n_neg,
+                                   const double* thr, int32_t n_thr, int64_t* out_counts,
+                                   unsigned long long* hist_ws, int sm_count, cudaStream_t stream);
+// K2.  q_bf16 is the prepared [n_q_padded, ldq] bf16 query matrix; handles up to 256 queries.
+cudaError_t launch_scan_mma(const ScanParams& p, const __nv_bfloat16* q_bf16, int32_t n_q_padded,
+                            int mode, int32_t* flags, int sm_count, cudaStream_t stream);
+int scan_mma_max_queries();
+bool scan_mma_available();
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define MMRS_CUDA(expr)                                                                     \
+  do {                                                                                      \
+    cudaError_t e__ = (expr);                                                               \
+    if (e__ != cudaSuccess)                                                                 \
+      return fail(MMRS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__),  \
+                  __FILE__, __LINE__);                                                      \
+  } while (0)
+
+struct DeviceInfo {
+  int device = -1;
+  int sm_count = 0;
+  int cc_major = 0;
+};
+
+static int current_device(DeviceInfo* info) {
+  static DeviceInfo cache[64];
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess)
+    return fail(MMRS_ERR_CUDA, "cudaGetDevice failed: %s (no CUDA device? this library has no CPU path)",
+                cudaGetErrorString(e));
+  if (dev < 0 || dev >= 64) return fail(MMRS_ERR_ARG, "device ordinal %d out of range", dev);
+  if (cache[dev].device != dev) {
+    DeviceInfo d;
+    d.device = dev;
+    MMRS_CUDA(cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+    MMRS_CUDA(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev));
+    cache[dev] = d;
+  }
+  *info = cache[dev];
+  if (info->cc_major != 10)
+    return fail(MMRS_ERR_ARCH, "device %d is compute capability %d.x; this library is sm_100a only",
+                dev, info->cc_major);
+  return MMRS_OK;
+}
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static int env_int(const char* name, int dflt) {
+  const char* s = getenv(name);
+  if (!s || !*s) return dflt;
+  return atoi(s);
+}
+
+constexpr int kSuperChunk = 1024;  // queries sharing one set of candidate lists
+
+static SearchPlan plan_for(int64_t n_rows, int32_t k) {
+  return make_search_plan(n_rows, k, kTileRows, env_int("MMRS_RATIO_LOG2", 4),
+                          env_int("MMRS_DENSE_TILES", 64));
+}
+
+static int32_t padded_dim(int32_t dim) { return (dim + 7) / 8 * 8; }
+static int32_t padded_queries(int32_t nq) { return (nq + 15) / 16 * 16; }
+
+struct Workspace {
+  int32_t* flags;          // [8]
+  float* q_f32;            // [Qp, ldq]
+  __nv_bfloat16* q_bf16;   // [Qp, ldq]
+  float* thr;              // [Qs]
+  uint32_t* cnt;           // [Qs]
+  uint64_t* cand;          // [Qs, cap] (>= n_tiles * kTileRows keys for the exhaustive path)
+  size_t cand_keys;
+  size_t total;
+};
+
+static Workspace carve(void* base, int64_t n_rows, int32_t dim, int32_t n_queries, int32_t k,
+                       bool with_lists) {
+  Workspace w{};
+  size_t off = 0;
+  char* b = static_cast<char*>(base);
+  auto take = [&](size_t bytes) { char* p = b ? b + off : nullptr; off += align_up(bytes, 256); return p; };
+  const int32_t ldq = padded_dim(dim), qp = padded_queries(n_queries);
+  w.flags = reinterpret_cast<int32_t*>(take(8 * sizeof(int32_t)));
+  w.q_f32 = reinterpret_cast<float*>(take(static_cast<size_t>(qp) * ldq * sizeof(float)));
+  w.q_bf16 = reinterpret_cast<__nv_bfloat16*>(take(static_cast<size_t>(qp) * ldq * sizeof(__nv_bfloat16)));
+  if (with_lists) {
+    const SearchPlan pl = plan_for(n_rows, k);
+    const int32_t qs = n_queries < kSuperChunk ? n_queries : kSuperChunk;
+    w.thr = reinterpret_cast<float*>(take(static_cast<size_t>(qs) * sizeof(float)));
+    w.cnt = reinterpret_cast<uint32_t*>(take(static_cast<size_t>(qs) * sizeof(uint32_t)));
+    size_t keys = static_cast<size_t>(qs) * pl.cap;
+    const size_t exhaustive = static_cast<size_t>(pl.n_tiles) * kTileRows;
+    if (keys < exhaustive) keys = exhaustive;
+    w.cand_keys = keys;
+    w.cand = reinterpret_cast<uint64_t*>(take(keys * sizeof(uint64_t)));
+  }
+  w.total = off;
+  return w;
+}
+
+static int check_matrix(const void* p, int64_t n_rows, int32_t dim, int64_t ld, int32_t dtype,
+                        const char* what) {
+  if (!p) return fail(MMRS_ERR_ARG, "%s pointer is null", what);
+  if (n_rows < 1) return fail(MMRS_ERR_ARG, "%s has %lld rows", what, (long long)n_rows);
+  if (n_rows > 0xffffffffll) return fail(MMRS_ERR_ARG, "%s: more than 2^32 rows per shard", what);
+  if (dtype != MMRS_DTYPE_F32 && dtype != MMRS_DTYPE_BF16)
+    return fail(MMRS_ERR_ARG, "%s dtype %d unknown", what, dtype);
+  const int elems16 = dtype == MMRS_DTYPE_BF16 ? 8 : 4;
+  if (dim < 1 || dim % elems16 != 0)
+    return fail(MMRS_ERR_ARG, "%s dim %d must be a positive multiple of %d (pad with zeros)", what,
+                dim, elems16);
+  if (ld < dim || ld % elems16 != 0)
+    return fail(MMRS_ERR_ARG, "%s row stride %lld must be >= dim and a multiple of %d", what,
+                (long long)ld, elems16);
+  if (reinterpret_cast<uintptr_t>(p) % 16 != 0)
+    return fail(MMRS_ERR_ARG, "%s pointer must be 16-byte aligned", what);
+  return MMRS_OK;
+}
+
+static int32_t* pinned_status() {
+  static thread_local int32_t* h = nullptr;
+  if (!h) {
+    if (cudaHostAlloc(reinterpret_cast<void**>(&h), 8 * sizeof(int32_t), cudaHostAllocDefault) != cudaSuccess)
+      h = nullptr;
+  }
+  return h;
+}
+
+enum class Path { kGemv, kMma };
+
+static Path choose_path(int32_t requested, int32_t dtype, int32_t n_queries) {
+  if (requested == MMRS_PATH_GEMV) return Path::kGemv;
+  if (requested == MMRS_PATH_MMA) return Path::kMma;
+  if (dtype == MMRS_DTYPE_BF16 && n_queries > 4 && scan_mma_available()) return Path::kMma;
+  return Path::kGemv;
+}
+
+// One scan over the tiles of `sched` for queries [q_lo, q_hi) of the prepared matrices.
+static int run_scan(Path path, const DeviceInfo& dev, int32_t dtype, ScanParams base,
+                    const Workspace& w, int32_t n_q_padded, int32_t q_lo, int32_t q_hi, int mode,
+                    cudaStream_t stream) {
+  if (path == Path::kMma) {
+    const int chunk = scan_mma_max_queries();
+    for (int32_t q = q_lo; q < q_hi; q += chunk) {
+      ScanParams p = base;
+      p.q0 = q;
+      p.nq = (q_hi - q) < chunk ? (q_hi - q) : chunk;
+      MMRS_CUDA(launch_scan_mma(p, w.q_bf16, n_q_padded, mode, w.flags, dev.sm_count, stream));
+    }
+    return MMRS_OK;
+  }
+  const int chunk = dtype == MMRS_DTYPE_F32 ? 8 : 4;
+  for (int32_t q = q_lo; q < q_hi; q += chunk) {
+    ScanParams p = base;
+    p.q0 = q;
+    p.nq = (q_hi - q) < chunk ? (q_hi - q) : chunk;
+    MMRS_CUDA(launch_scan_gemv(p, dtype, mode, dev.sm_count, stream));
+  }
+  return MMRS_OK;
+}
+
+static TileSchedule sched_of(const SearchPlan& pl, int i) {
+  TileSchedule s;
+  s.n_tiles = pl.n_tiles;
+  s.tile_inc = pl.phase[i].inc;
+  s.tile_exc = pl.phase[i].exc;
+  s.n_sel = pl.phase[i].n_sel;
+  return s;
+}
+
+struct SearchArgs {
+  const void* gallery; int64_t n_rows; int32_t dim; int64_t ld; int32_t dtype;
+  const float* d_queries; int32_t n_queries; int64_t ldq_in;
+  int32_t k; int32_t normalize; float scale; int64_t index_offset; int32_t path;
+  float* d_values; int64_t* d_indices;
+};
+
+// Enqueue the whole fused search on `stream`.  Results are valid iff the flag word stays 0.
+static int enqueue_search(const SearchArgs& a, const DeviceInfo& dev, const Workspace& w,
+                          cudaStream_t stream) {
+  const SearchPlan pl = plan_for(a.n_rows, a.k);
+  const int32_t ldq = padded_dim(a.dim), qp = padded_queries(a.n_queries);
+  const Path path = choose_path(a.path, a.dtype, a.n_queries);
+  if (path == Path::kMma && a.dtype != MMRS_DTYPE_BF16)
+    return fail(MMRS_ERR_ARG, "MMRS_PATH_MMA needs a bf16 gallery");
+
+  MMRS_CUDA(cudaMemsetAsync(w.flags, 0, 8 * sizeof(int32_t), stream));
+  MMRS_CUDA(launch_prep_queries(a.d_queries, a.n_queries, a.ldq_in, a.dim, a.normalize,
+                                a.dtype == MMRS_DTYPE_BF16, w.q_f32, w.q_bf16, qp, ldq, w.flags,
+                                stream));
+  ScanParams base{};
+  base.gallery = a.gallery; base.n_rows = a.n_rows; base.ld = a.ld; base.dim = a.dim;
+  base.queries = w.q_f32; base.ldq = ldq; base.scale = a.scale;
+  base.cap = pl.cap;
+
+  for (int32_t s0 = 0; s0 < a.n_queries; s0 += kSuperChunk) {
+    const int32_t s1 = (a.n_queries - s0) < kSuperChunk ? a.n_queries : s0 + kSuperChunk;
+    const int32_t ns = s1 - s0;
+    // list q of this super-chunk lives at cand[(q - s0) * cap]: bias the pointers so kernels
+    // can index by absolute query id
+    base.cand = w.cand - static_cast<int64_t>(s0) * pl.cap;
+    base.cnt = w.cnt - s0;
+    base.thr = w.thr - s0;
+    for (int ph = 0; ph < pl.n_phases; ++ph) {
+      base.sched = sched_of(pl, ph);
+      const int mode = ph == 0 ? kModeDense : kModeFilter;
+      int rc = run_scan(path, dev, a.dtype, base, w, qp, s0, s1, mode, stream);
+      if (rc != MMRS_OK) return rc;
+      SelectParams sp{};
+      sp.cand = w.cand; sp.cnt = w.cnt; sp.thr = w.thr; sp.cap = pl.cap;
+      sp.fixed_n = ph == 0 ? pl.dense_rows : -1;
+      sp.k = a.k;
+      sp.final_pass = ph == pl.n_phases - 1;
+      sp.out_values = a.d_values + static_cast<int64_t>(s0) * a.k;
+      sp.out_indices = a.d_indices + static_cast<int64_t>(s0) * a.k;
+      sp.index_offset = a.index_offset;
+      sp.flags = w.flags;
+      MMRS_CUDA(launch_select(sp, ns, stream));
+    }
+  }
+  return MMRS_OK;
+}
+
+// Slow exact path for when a candidate list overflowed: one query at a time, every score
+// becomes a key, one select over all of them.
+static int enqueue_exhaustive(const SearchArgs& a, const DeviceInfo& dev, const Workspace& w,
+                              cudaStream_t stream) {
+  const SearchPlan pl = plan_for(a.n_rows, a.k);
+  const int32_t ldq = padded_dim(a.dim);
+  const int32_t all_rows = pl.n_tiles * kTileRows;
+  ScanParams base{};
+  base.gallery = a.gallery; base.n_rows = a.n_rows; base.ld = a.ld; base.dim = a.dim;
+  base.queries = w.q_f32; base.ldq = ldq; base.scale = a.scale;
+  base.cap = all_rows;
+  base.sched = TileSchedule{pl.n_tiles, 1, 0, pl.n_tiles};
+  MMRS_CUDA(cudaMemsetAsync(w.flags, 0, 8 * sizeof(int32_t), stream));
+  for (int32_t q = 0; q < a.n_queries; ++q) {
+    ScanParams p = base;
+    p.cand = w.cand - static_cast<int64_t>(q) * all_rows;
+    p.q0 = q; p.nq = 1;
+    MMRS_CUDA(launch_scan_gemv(p, a.dtype, kModeDense, dev.sm_count, stream));
+    SelectParams sp{};
+    sp.cand = w.cand; sp.cnt = w.cnt; sp.thr = w.thr; sp.cap = all_rows;
+    sp.fixed_n = all_rows; sp.k = a.k; sp.final_pass = 1;
+    sp.out_values = a.d_values + static_cast<int64_t>(q) * a.k;
+    sp.out_indices = a.d_indices + static_cast<int64_t>(q) * a.k;
+    sp.index_offset = a.index_offset; sp.flags = w.flags;
+    MMRS_CUDA(launch_select(sp, 1, stream));
+  }
+  return MMRS_OK;
+}
+
+static int flags_to_status(int32_t f) {
+  if (f & kFlagZeroNorm)
+    return fail(MMRS_ERR_ZERO_NORM, "a query row has zero L2 norm and normalize_queries is set");
+  if (f & kFlagWatchdog) return fail(MMRS_ERR_INTERNAL, "K2 pipeline watchdog fired (mbarrier wait timed out)");
+  if (f & kFlagShort) return fail(MMRS_ERR_INTERNAL, "select saw fewer than k unique candidates");
+  if (f & kFlagOverflow) return fail(MMRS_ERR_INTERNAL, "candidate list overflow");
+  return MMRS_OK;
+}
+
+static int validate_search(const SearchArgs& a, const void* ws, size_t ws_bytes, size_t extra) {
+  int rc = check_matrix(a.gallery, a.n_rows, a.dim, a.ld, a.dtype, "gallery");
+  if (rc != MMRS_OK) return rc;
+  if (a.n_queries < 0) return fail(MMRS_ERR_ARG, "n_queries < 0");
+  if (a.k < 1 || a.k > 1024) return fail(MMRS_ERR_ARG, "k = %d must be in [1, 1024]", a.k);
+  if (a.k > a.n_rows)
+    return fail(MMRS_ERR_ARG, "k = %d exceeds the %lld gallery rows (torch.topk raises here too)",
+                a.k, (long long)a.n_rows);
+  if (a.ldq_in < a.dim) return fail(MMRS_ERR_ARG, "query row stride < dim");
+  const size_t need = mmrs_search_workspace_bytes(a.n_rows, a.dim, a.dtype, a.n_queries, a.k) + extra;
+  if (!ws || ws_bytes < need)
+    return fail(MMRS_ERR_WORKSPACE, "workspace %zu bytes, need %zu", ws_bytes, need);
+  if (reinterpret_cast<uintptr_t>(ws) % 256 != 0)
+    return fail(MMRS_ERR_WORKSPACE, "workspace must be 256-byte aligned");
+  return MMRS_OK;
+}
+
+}  // namespace mmrs
+
+using namespace mmrs;
+
+extern "C" {
+
+int mmrs_abi_version(void) { return MMRS_ABI_VERSION; }
+const char* mmrs_last_error(void) { return g_err; }
+
+int mmrs_device_check(int device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess)
+    return fail(MMRS_ERR_CUDA, "cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
+  if (device < 0 || device >= count)
+    return fail(MMRS_ERR_ARG, "device %d not present (%d visible)", device, count);
+  int major = 0;
+  MMRS_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  if (major != 10)
+    return fail(MMRS_ERR_ARCH, "device %d is compute capability %d.x; sm_100a required", device, major);
+  return MMRS_OK;
+}
+
+size_t mmrs_full_scores_workspace_bytes(int64_t n_rows, int32_t dim, int32_t gallery_dtype,
+                                        int32_t n_queries) {
+  (void)gallery_dtype;
+  return carve(nullptr, n_rows, dim, n_queries, 1, false).total;
+}
+
+int mmrs_full_scores(const void* d_gallery, int64_t n_rows, int32_t dim, int64_t ld_gallery,
+                     int32_t gallery_dtype, const float* d_queries, int32_t n_queries,
+                     int64_t ld_queries, int32_t normalize_queries, float scale, int32_t path,
+                     float* d_out_scores, int64_t ld_out, void* d_workspace,
+                     size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceInfo dev;
+  int rc = current_device(&dev);
+  if (rc != MMRS_OK) return rc;
+  rc = check_matrix(d_gallery, n_rows, dim, ld_gallery, gallery_dtype, "gallery");
+  if (rc != MMRS_OK) return rc;
+  if (n_queries == 0) return MMRS_OK;
+  if (n_queries < 0 || !d_queries || !d_out_scores || ld_out < n_rows || ld_queries < dim)
+    return fail(MMRS_ERR_ARG, "bad query / output arguments");
+  const size_t need = mmrs_full_scores_workspace_bytes(n_rows, dim, gallery_dtype, n_queries);
+  if (!d_workspace || workspace_bytes < need || reinterpret_cast<uintptr_t>(d_workspace) % 256)
+    return fail(MMRS_ERR_WORKSPACE, "workspace %zu bytes, need %zu (256-byte aligned)", workspace_bytes, need);
+  const Workspace w = carve(d_workspace, n_rows, dim, n_queries, 1, false);
+  const int32_t ldq = padded_dim(dim), qp = padded_queries(n_queries);
+  const Path p = choose_path(path, gallery_dtype, n_queries);
+  if (p == Path::kMma && gallery_dtype != MMRS_DTYPE_BF16)
+    return fail(MMRS_ERR_ARG, "MMRS_PATH_MMA needs a bf16 gallery");
+  MMRS_CUDA(cudaMemsetAsync(w.flags, 0, 8 * sizeof(int32_t), stream));
+  MMRS_CUDA(launch_prep_queries(d_queries, n_queries, ld_queries, dim, normalize_queries,
+                                gallery_dtype == MMRS_DTYPE_BF16, w.q_f32, w.q_bf16, qp, ldq,
+                                w.flags, stream));
+  ScanParams base{};
+  base.gallery = d_gallery; base.n_rows = n_rows; base.ld = ld_gallery; base.dim = dim;
+  base.queries = w.q_f32; base.ldq = ldq; base.scale = scale;
+  base.out_scores = d_out_scores; base.ld_out = ld_out;
+  const int32_t n_tiles = static_cast<int32_t>((n_rows + kTileRows - 1) / kTileRows);
+  base.sched = TileSchedule{n_tiles, 1, 0, n_tiles};
+  rc = run_scan(p, dev, gallery_dtype, base, w, qp, 0, n_queries, kModeScores, stream);
+  if (rc != MMRS_OK) return rc;
+  int32_t* h = pinned_status();
+  if (!h) return fail(MMRS_ERR_CUDA, "cudaHostAlloc for the status word failed");
+  MMRS_CUDA(cudaMemcpyAsync(h, w.flags, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  MMRS_CUDA(cudaStreamSynchronize(stream));
+  return flags_to_status(h[0]);
+}
+
+size_t mmrs_search_workspace_bytes(int64_t n_rows, int32_t dim, int32_t gallery_dtype,
+                                   int32_t n_queries, int32_t k) {
+  (void)gallery_dtype;
+  if (n_rows < 1 || dim < 1 || n_queries < 0 || k < 1) return 0;
+  return carve(nullptr, n_rows, dim, n_queries < 1 ? 1 : n_queries, k, true).total;
+}
+
+size_t mmrs_search_host_staging_bytes(int32_t dim, int32_t n_queries, int32_t k) {
+  if (n_queries < 1) n_queries = 1;
+  return align_up(static_cast<size_t>(n_queries) * dim * sizeof(float), 256) +
+         align_up(static_cast<size_t>(n_queries) * k * sizeof(float), 256) +
+         align_up(static_cast<size_t>(n_queries) * k * sizeof(int64_t), 256);
+}
+
+static int search_common(SearchArgs a, const float* h_queries, float* h_values, int64_t* h_indices,
+                         void* d_workspace, size_t workspace_bytes, cudaStream_t stream) {
+  DeviceInfo dev;
+  int rc = current_device(&dev);
+  if (rc != MMRS_OK) return rc;
+  const bool host_io = h_queries != nullptr;
+  const size_t staging = host_io ? mmrs_search_host_staging_bytes(a.dim, a.n_queries, a.k) : 0;
+  rc = validate_search(a, d_workspace, workspace_bytes, staging);
+  if (rc != MMRS_OK) return rc;
+  if (a.n_queries == 0) return MMRS_OK;
+  if (!host_io && (!a.d_queries || !a.d_values || !a.d_indices))
+    return fail(MMRS_ERR_ARG, "null query / output pointer");
+  const Workspace w = carve(d_workspace, a.n_rows, a.dim, a.n_queries, a.k, true);
+  const size_t vbytes = static_cast<size_t>(a.n_queries) * a.k * sizeof(float);
+  const size_t ibytes = static_cast<size_t>(a.n_queries) * a.k * sizeof(int64_t);
+  if (host_io) {
+    if (!h_values || !h_indices) return fail(MMRS_ERR_ARG, "null host output pointer");
+    char* s = static_cast<char*>(d_workspace) + w.total;
+    float* dq = reinterpret_cast<float*>(s);
+    s += align_up(static_cast<size_t>(a.n_queries) * a.dim * sizeof(float), 256);
+    a.d_values = reinterpret_cast<float*>(s);
+    s += align_up(vbytes, 256);
+    a.d_indices = reinterpret_cast<int64_t*>(s);
+    MMRS_CUDA(cudaMemcpy2DAsync(dq, static_cast<size_t>(a.dim) * sizeof(float), h_queries,
+                                static_cast<size_t>(a.ldq_in) * sizeof(float),
+                                static_cast<size_t>(a.dim) * sizeof(float), a.n_queries,
+                                cudaMemcpyHostToDevice, stream));
+    a.d_queries = dq;
+    a.ldq_in = a.dim;
+  }
+  rc = enqueue_search(a, dev, w, stream);
+  if (rc != MMRS_OK) return rc;
+  int32_t* h = pinned_status();
+  if (!h) return fail(MMRS_ERR_CUDA, "cudaHostAlloc for the status word failed");
+  MMRS_CUDA(cudaMemcpyAsync(h, w.flags, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  if (host_io) {
+    MMRS_CUDA(cudaMemcpyAsync(h_values, a.d_values, vbytes, cudaMemcpyDeviceToHost, stream));
+    MMRS_CUDA(cudaMemcpyAsync(h_indices, a.d_indices, ibytes, cudaMemcpyDeviceToHost, stream));
+  }
+  MMRS_CUDA(cudaStreamSynchronize(stream));
+  int32_t f = h[0];
+  if (f == kFlagOverflow) {
+    // exact but slow: rerun every query exhaustively (rare: needs scores correlated with the
+    // tile stride pattern)
+    rc = enqueue_exhaustive(a, dev, w, stream);
+    if (rc != MMRS_OK) return rc;
+    MMRS_CUDA(cudaMemcpyAsync(h, w.flags, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    if (host_io) {
+      MMRS_CUDA(cudaMemcpyAsync(h_values, a.d_values, vbytes, cudaMemcpyDeviceToHost, stream));
+      MMRS_CUDA(cudaMemcpyAsync(h_indices, a.d_indices, ibytes, cudaMemcpyDeviceToHost, stream));
+    }
+    MMRS_CUDA(cudaStreamSynchronize(stream));
+    f = h[0];
+  }
+  return flags_to_status(f);
+}
+
+int mmrs_search_topk(const void* d_gallery, int64_t n_rows, int32_t dim, int64_t ld_gallery,
+                     int32_t gallery_dtype, const float* d_queries, int32_t n_queries,
+                     int64_t ld_queries, int32_t k, int32_t normalize_queries, float scale,
+                     int64_t index_offset, int32_t path, float* d_out_values,
+                     int64_t* d_out_indices, void* d_workspace, size_t workspace_bytes,
+                     void* stream) {
+  SearchArgs a{d_gallery, n_rows, dim, ld_gallery, gallery_dtype, d_queries, n_queries, ld_queries,
+               k, normalize_queries, scale, index_offset, path, d_out_values, d_out_indices};
+  return search_common(a, nullptr, nullptr, nullptr, d_workspace, workspace_bytes,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int mmrs_search_topk_host(const void* d_gallery, int64_t n_rows, int32_t dim, int64_t ld_gallery,
+                          int32_t gallery_dtype, const float* h_queries, int32_t n_queries,
+                          int64_t ld_queries, int32_t k, int32_t normalize_queries, float scale,
+                          int64_t index_offset, int32_t path, float* h_out_values,
+                          int64_t* h_out_indices, void* d_workspace, size_t workspace_bytes,
+                          void* stream) {
+  if (n_queries > 0 && !h_queries) return fail(MMRS_ERR_ARG, "null host query pointer");
+  SearchArgs a{d_gallery, n_rows, dim, ld_gallery, gallery_dtype, nullptr, n_queries, ld_queries,
+               k, normalize_queries, scale, index_offset, path, nullptr, nullptr};
+  if (n_queries == 0) {
+    static const float dummy = 0.f;
+    h_queries = &dummy;
+  }
+  return search_common(a, h_queries, h_out_values, h_out_indices, d_workspace, workspace_bytes,
+                       static_cast<cudaStream_t>(stream));
+}
+
+size_t mmrs_topk_merge_workspace_bytes(int32_t n_lists, int32_t n_queries, int32_t k_in) {
+  if (n_lists < 1 || n_queries < 1 || k_in < 1) return 256;
+  return align_up(8 * sizeof(int32_t), 256) +
+         align_up(static_cast<size_t>(n_queries) * n_lists * k_in * sizeof(uint64_t), 256);
+}
+
+int mmrs_topk_merge(const float* d_values_in, const int64_t* d_indices_in, int32_t n_lists,
+                    int32_t n_queries, int32_t k_in, int32_t k_out, float* d_out_values,
+                    int64_t* d_out_indices, void* d_workspace, size_t workspace_bytes,
+                    void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceInfo dev;
+  int rc = current_device(&dev);
+  if (rc != MMRS_OK) return rc;
+  if (n_queries == 0) return MMRS_OK;
+  if (n_lists < 1 || n_queries < 0 || k_in < 1 || k_out < 1 || k_out > 1024 ||
+      static_cast<int64_t>(n_lists) * k_in < k_out)
+    return fail(MMRS_ERR_ARG, "bad merge shape: %d lists x %d, k_out %d", n_lists, k_in, k_out);
+  if (!d_values_in || !d_indices_in || !d_out_values || !d_out_indices)
+    return fail(MMRS_ERR_ARG, "null pointer");
+  const size_t need = mmrs_topk_merge_workspace_bytes(n_lists, n_queries, k_in);
+  if (!d_workspace || workspace_bytes < need || reinterpret_cast<uintptr_t>(d_workspace) % 256)
+    return fail(MMRS_ERR_WORKSPACE, "workspace %zu bytes, need %zu (256-byte aligned)", workspace_bytes, need);
+  int32_t* flags = static_cast<int32_t*>(d_workspace);
+  uint64_t* cand = reinterpret_cast<uint64_t*>(static_cast<char*>(d_workspace) + align_up(8 * sizeof(int32_t), 256));
+  const int32_t cap = n_lists * k_in;
+  MMRS_CUDA(cudaMemsetAsync(flags, 0, 8 * sizeof(int32_t), stream));
+  MMRS_CUDA(launch_pack_keys(d_values_in, d_indices_in, n_lists, n_queries, k_in, cand, cap, stream));
+  SelectParams sp{};
+  sp.cand = cand; sp.cnt = nullptr; sp.thr = nullptr; sp.cap = cap; sp.fixed_n = cap;
+  sp.k = k_out; sp.final_pass = 1; sp.out_values = d_out_values; sp.out_indices = d_out_indices;
+  sp.index_offset = 0; sp.flags = flags;
+  MMRS_CUDA(launch_select(sp, n_queries, stream));
+  int32_t* h = pinned_status();
+  if (!h) return fail(MMRS_ERR_CUDA, "cudaHostAlloc for the status word failed");
+  MMRS_CUDA(cudaMemcpyAsync(h, flags, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  MMRS_CUDA(cudaStreamSynchronize(stream));
+  return flags_to_status(h[0]);
+}
+
+size_t mmrs_selfjoin_workspace_bytes(int64_t n_rows, int32_t dim, int32_t dtype) {
+  (void)n_rows; (void)dim; (void)dtype;
+  return 256;
+}
+
+int mmrs_selfjoin_pairs(const void* d_emb, int64_t n_rows, int32_t dim, int64_t ld_emb,
+                        int32_t dtype, float threshold, int64_t row_begin, int64_t row_end,
+                        int64_t* d_out_pairs, int64_t capacity, int64_t* d_out_count,
+                        void* d_workspace, size_t workspace_bytes, void* stream_) {
+  (void)d_workspace; (void)workspace_bytes;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceInfo dev;
+  int rc = current_device(&dev);
+  if (rc != MMRS_OK) return rc;
+  rc = check_matrix(d_emb, n_rows, dim, ld_emb, dtype, "embeddings");
+  if (rc != MMRS_OK) return rc;
+  if (dtype != MMRS_DTYPE_F32) return fail(MMRS_ERR_ARG, "self-join exact mode takes fp32 embeddings");
+  if (dim % 8 != 0) return fail(MMRS_ERR_ARG, "self-join dim must be a multiple of 8 (pad with zeros)");
+  if (row_begin < 0 || row_end > n_rows || row_begin > row_end || row_begin % 128 != 0)
+    return fail(MMRS_ERR_ARG, "row range [%lld, %lld) invalid (begin must be a multiple of 128)",
+                (long long)row_begin, (long long)row_end);
+  if (capacity < 0 || (capacity > 0 && !d_out_pairs) || !d_out_count)
+    return fail(MMRS_ERR_ARG, "bad output arguments");
+  MMRS_CUDA(cudaMemsetAsync(d_out_count, 0, sizeof(int64_t), stream));
+  MMRS_CUDA(launch_selfjoin_f32(static_cast<const float*>(d_emb), n_rows, dim, ld_emb, threshold,
+                                row_begin, row_end, d_out_pairs, capacity, d_out_count,
+                                dev.sm_count, stream));
+  int32_t* h = pinned_status();
+  if (!h) return fail(MMRS_ERR_CUDA, "cudaHostAlloc for the status word failed");
+  int64_t* h64 = reinterpret_cast<int64_t*>(h);
+  MMRS_CUDA(cudaMemcpyAsync(h64, d_out_count, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+  MMRS_CUDA(cudaStreamSynchronize(stream));
+  if (h64[0] > capacity)
+    return fail(MMRS_ERR_CAPACITY, "%lld pairs found, capacity %lld", (long long)h64[0], (long long)capacity);
+  return MMRS_OK;
+}
+
+size_t mmrs_threshold_sweep_workspace_bytes(int32_t n_thresholds) {
+  if (n_thresholds < 1) n_thresholds = 1;
+  return align_up(sizeof(unsigned long long) * 2 * (static_cast<size_t>(n_thresholds) + 1), 256);
+}
+
+int mmrs_threshold_sweep(const float* d_pos, int64_t n_pos, const float* d_neg, int64_t n_neg,
+                         const double* d_thresholds, int32_t n_thresholds, int64_t* d_out_counts,
+                         void* d_workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceInfo dev;
+  int rc = current_device(&dev);
+  if (rc != MMRS_OK) return rc;
+  if (n_thresholds < 1 || n_thresholds > 4096) return fail(MMRS_ERR_ARG, "n_thresholds must be in [1, 4096]");
+  if (n_pos < 0 || n_neg < 0 || (n_pos > 0 && !d_pos) || (n_neg > 0 && !d_neg) || !d_thresholds || !d_out_counts)
+    return fail(MMRS_ERR_ARG, "bad arguments");
+  if (!d_workspace || workspace_bytes < mmrs_threshold_sweep_workspace_bytes(n_thresholds))
+    return fail(MMRS_ERR_WORKSPACE, "workspace too small");
+  MMRS_CUDA(launch_threshold_sweep(d_pos, n_pos, d_neg, n_neg, d_thresholds, n_thresholds,
+                                   d_out_counts, static_cast<unsigned long long*>(d_workspace),
+                                   dev.sm_count, stream));
+  return MMRS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,127 @@
+// common.cuh -- shared device/host helpers for the mmrs_b200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mmrs_b200.h"
+
+namespace mmrs {
+
+// Every scan kernel walks the gallery in row tiles of this many rows; the phase
+// schedule (api.cu) is expressed in tiles.
+constexpr int kTileRows = 128;
+
+// Status bits a kernel can raise in the device-side flag word.
+constexpr int kFlagOverflow = 1;      // a candidate list outgrew its capacity
+constexpr int kFlagZeroNorm = 2;      // normalize_queries and ||q|| == 0
+constexpr int kFlagShort = 4;         // fewer than k candidates reached a select (bug guard)
+constexpr int kFlagWatchdog = 8;      // an mbarrier wait timed out (K2 debug guard)
+
+// ---- order-preserving (score, row) -> u64 key ---------------------------------------------
+// Larger key == better match: higher score first, then LOWER row index.  Keys are unique
+// because row indices are, so "the k largest keys" is a deterministic set and order -- this is
+// the tie rule of SURVEY.md H1 (score desc, index asc == stable descending sort).
+__host__ __device__ __forceinline__ uint32_t orderable_from_float(float f) {
+#ifdef __CUDA_ARCH__
+  uint32_t u = __float_as_uint(f);
+#else
+  union { float f; uint32_t u; } c; c.f = f; uint32_t u = c.u;
+#endif
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float float_from_orderable(uint32_t o) {
+  uint32_t u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  union { float f; uint32_t u; } c; c.u = u; return c.f;
+#endif
+}
+__host__ __device__ __forceinline__ uint64_t make_key(float score, uint32_t row) {
+  score += 0.0f;  // -0.0 -> +0.0: the two compare equal, so they must tie (and fall to the index)
+  return (static_cast<uint64_t>(orderable_from_float(score)) << 32) | static_cast<uint64_t>(~row);
+}
+__host__ __device__ __forceinline__ float key_score(uint64_t key) {
+  return float_from_orderable(static_cast<uint32_t>(key >> 32));
+}
+__host__ __device__ __forceinline__ uint32_t key_row(uint64_t key) {
+  return ~static_cast<uint32_t>(key);
+}
+
+// ---- streaming loads -------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ldg_stream_16B(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+// ---- epilogue modes of the scan kernels ---------------------------------------------------
+enum ScanMode : int {
+  kModeScores = 0,  // write fp32 scores to out[q, row]                  (full_scores)
+  kModeDense = 1,   // write every key at a fixed slot, no atomics         (seed phase)
+  kModeFilter = 2   // append keys whose score passes thr[q] (atomic slot) (later phases)
+};
+
+// Which tiles a launch covers: t = j * tile_inc for j in [0, n_sel), skipping t with
+// t % tile_exc == 0 when tile_exc != 0 (those were covered by an earlier phase).
+struct TileSchedule {
+  int32_t n_tiles;   // ceil(n_rows / kTileRows)
+  int32_t tile_inc;
+  int32_t tile_exc;
+  int32_t n_sel;     // ceil(n_tiles / tile_inc)
+};
+
+struct ScanParams {
+  const void* gallery;    // [n_rows, ld] T
+  int64_t n_rows;
+  int64_t ld;             // elements
+  int32_t dim;
+  const float* queries;   // prepared fp32 queries [*, ldq] (normalised, bf16-rounded in bf16 mode)
+  int32_t ldq;
+  int32_t q0;             // first query of this pass
+  int32_t nq;             // queries in this pass (<= template QN)
+  float scale;
+  TileSchedule sched;
+  // kModeScores
+  float* out_scores;
+  int64_t ld_out;
+  // kModeDense / kModeFilter
+  uint64_t* cand;         // [n_queries, cap] keys
+  uint32_t* cnt;          // [n_queries]
+  const float* thr;       // [n_queries] current lower bound on the k-th best score
+  int32_t cap;
+};
+
+struct SelectParams {
+  uint64_t* cand;         // [n_queries, cap]
+  uint32_t* cnt;          // [n_queries]; used when fixed_n < 0
+  float* thr;             // [n_queries] out: score of the k-th best
+  int32_t cap;
+  int32_t fixed_n;        // >= 0: every list has exactly this many entries
+  int32_t k;
+  int32_t final_pass;     // 1: write out_values / out_indices; 0: compact list + thr
+  float* out_values;      // [n_queries, k]
+  int64_t* out_indices;   // [n_queries, k]
+  int64_t index_offset;
+  int32_t* flags;
+};
+
+// launchers (defined in the .cu files, called from api.cu)
+cudaError_t launch_prep_queries(const float* q, int32_t n_queries, int64_t ldq, int32_t dim,
+                                int32_t normalize, int32_t round_bf16, float* out_f32,
+                                __nv_bfloat16* out_bf16, int32_t n_rows_padded, int32_t ld_out,
+                                int32_t* flags, cudaStream_t stream);
+cudaError_t launch_scan_gemv(const ScanParams& p, int32_t dtype, int mode, int sm_count,
+                             cudaStream_t stream);
+cudaError_t launch_select(const SelectParams& p, int32_t n_queries, cudaStream_t stream);
+cudaError_t launch_fill_u32(uint32_t* p, uint32_t v, int64_t n, cudaStream_t stream);
+cudaError_t launch_fill_f32(float* p, float v, int64_t n, cudaStream_t stream);
+cudaError_t launch_pack_keys(const float* values, const int64_t* indices, int32_t n_lists,
+                             int32_t n_queries, int32_t k_in, uint64_t* cand, int32_t cap,
+                             cudaStream_t stream);
+
+}  // namespace mmrs

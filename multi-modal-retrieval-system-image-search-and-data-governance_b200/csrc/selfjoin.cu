@@ -1,0 +1,199 @@
+// selfjoin.cu -- K5 (exact fp32 mode): thresholded embedding self-join.
+//
+// The reference's near-duplicate tools compare every image with every kept representative in
+// an interpreted double loop (tool/find_repeated_in_same_folder.py:76-95,
+// tool/delete repeated.py:127-135).  BASELINE.json replaces the perceptual-hash predicate by
+// cos(e_i, e_j) >= tau on unit-norm CLIP embeddings; this kernel evaluates that predicate for
+// every pair i < j of an upper-triangular 128x128 block schedule and appends the hits.
+//
+// Exact mode: fp32 FFMA, k ascending, one accumulator per pair -- the pair set does not depend
+// on tile shape or launch geometry.  (The tensor-core prefilter + exact recheck variant lives in
+// selfjoin_mma.cu once K2's pipeline is proven.)
+#include "common.cuh"
+
+namespace mmrs {
+
+constexpr int kSjTile = 128;   // rows of each side per CTA tile
+constexpr int kSjBK = 8;       // k-slice staged per iteration
+constexpr int kSjThreads = 256;
+
+struct SelfJoinParams {
+  const float* emb;
+  int64_t n_rows;
+  int64_t ld;
+  int32_t dim;
+  float threshold;
+  int64_t bi_begin, bi_end;   // row-block range of the "i" side owned by this call
+  int64_t nb;                 // number of row blocks
+  int64_t total_tiles;
+  int64_t* out_pairs;
+  int64_t capacity;
+  unsigned long long* out_count;
+};
+
+// tiles are numbered row-block by row-block: block row bi owns (nb - bi) tiles (bj = bi..nb-1)
+__device__ __forceinline__ void decode_tile(int64_t t, int64_t bi0, int64_t nb, int64_t& bi,
+                                            int64_t& bj) {
+  // tiles before block row b (relative to bi0): f(b) = sum_{x=bi0}^{b-1} (nb - x)
+  const double m = static_cast<double>(nb - bi0);
+  // solve f(b) <= t: with r = b - bi0, f = r*m - r(r-1)/2
+  double r = floor((2.0 * m + 1.0 - sqrt((2.0 * m + 1.0) * (2.0 * m + 1.0) - 8.0 * static_cast<double>(t))) * 0.5);
+  int64_t ri = static_cast<int64_t>(r);
+  if (ri < 0) ri = 0;
+  auto f = [&](int64_t x) { return x * (nb - bi0) - x * (x - 1) / 2; };
+  while (ri > 0 && f(ri) > t) --ri;
+  while (f(ri + 1) <= t) ++ri;
+  bi = bi0 + ri;
+  bj = bi + (t - f(ri));
+}
+
+__global__ void __launch_bounds__(kSjThreads) selfjoin_f32_kernel(const SelfJoinParams p) {
+  __shared__ __align__(16) float As[kSjBK][kSjTile];
+  __shared__ __align__(16) float Bs[kSjBK][kSjTile];
+  const int tid = threadIdx.x;
+  const int ty = tid / 16, tx = tid % 16;
+  const int ld_row = tid / 2, ld_k = (tid % 2) * 4;
+
+  for (int64_t t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+    int64_t bi, bj;
+    decode_tile(t, p.bi_begin, p.nb, bi, bj);
+    const int64_t i0 = bi * kSjTile, j0 = bj * kSjTile;
+    const int64_t arow = min(i0 + ld_row, p.n_rows - 1);
+    const int64_t brow = min(j0 + ld_row, p.n_rows - 1);
+    const float* ap = p.emb + arow * p.ld + ld_k;
+    const float* bp = p.emb + brow * p.ld + ld_k;
+
+    float acc[8][8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+      for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
+
+    for (int k0 = 0; k0 < p.dim; k0 += kSjBK) {
+      const float4 av = *reinterpret_cast<const float4*>(ap + k0);
+      const float4 bv = *reinterpret_cast<const float4*>(bp + k0);
+      __syncthreads();
+      As[ld_k + 0][ld_row] = av.x; As[ld_k + 1][ld_row] = av.y;
+      As[ld_k + 2][ld_row] = av.z; As[ld_k + 3][ld_row] = av.w;
+      Bs[ld_k + 0][ld_row] = bv.x; Bs[ld_k + 1][ld_row] = bv.y;
+      Bs[ld_k + 2][ld_row] = bv.z; Bs[ld_k + 3][ld_row] = bv.w;
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < kSjBK; ++kk) {
+        const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 8]);
+        const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][ty * 8 + 4]);
+        const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 8]);
+        const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 8 + 4]);
+        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int x = 0; x < 8; ++x)
+#pragma unroll
+          for (int y = 0; y < 8; ++y) acc[x][y] = fmaf(a[x], b[y], acc[x][y]);
+      }
+    }
+
+#pragma unroll
+    for (int x = 0; x < 8; ++x)
+#pragma unroll
+      for (int y = 0; y < 8; ++y) {
+        const int64_t i = i0 + ty * 8 + x, j = j0 + tx * 8 + y;
+        if (i < j && j < p.n_rows && acc[x][y] >= p.threshold) {
+          const unsigned long long pos = atomicAdd(p.out_count, 1ull);
+          if (pos < static_cast<unsigned long long>(p.capacity)) {
+            p.out_pairs[2 * pos] = i;
+            p.out_pairs[2 * pos + 1] = j;
+          }
+        }
+      }
+  }
+}
+
+cudaError_t launch_selfjoin_f32(const float* emb, int64_t n_rows, int32_t dim, int64_t ld,
+                                float threshold, int64_t row_begin, int64_t row_end,
+                                int64_t* out_pairs, int64_t capacity, int64_t* out_count,
+                                int sm_count, cudaStream_t stream) {
+  SelfJoinParams p{};
+  p.emb = emb; p.n_rows = n_rows; p.ld = ld; p.dim = dim; p.threshold = threshold;
+  p.nb = (n_rows + kSjTile - 1) / kSjTile;
+  p.bi_begin = row_begin / kSjTile;
+  p.bi_end = (row_end + kSjTile - 1) / kSjTile;
+  if (p.bi_end > p.nb) p.bi_end = p.nb;
+  const int64_t nbi = p.bi_end - p.bi_begin;
+  if (nbi <= 0) return cudaSuccess;
+  p.total_tiles = nbi * (p.nb - p.bi_begin) - nbi * (nbi - 1) / 2;
+  p.out_pairs = out_pairs; p.capacity = capacity;
+  p.out_count = reinterpret_cast<unsigned long long*>(out_count);
+  int64_t grid = static_cast<int64_t>(sm_count) * 2;
+  if (grid > p.total_tiles) grid = p.total_tiles;
+  selfjoin_f32_kernel<<<static_cast<int>(grid), kSjThreads, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+// ---- threshold sweep (code/search_image.py:39-79) ------------------------------------------------
+// counts[t] = (#pos >= thr_t, #neg >= thr_t) for an ASCENDING threshold grid: each score finds
+// how many thresholds it reaches by binary search (fp64 compare, as numpy promotes), bumps one
+// histogram bin, and a suffix sum turns the histogram into the counts.
+constexpr int kSweepMaxT = 4096;
+
+__global__ void __launch_bounds__(256) sweep_hist_kernel(const float* __restrict__ pos, int64_t n_pos,
+                                                         const float* __restrict__ neg, int64_t n_neg,
+                                                         const double* __restrict__ thr, int32_t n_thr,
+                                                         unsigned long long* __restrict__ hist) {
+  extern __shared__ double s_thr[];                  // [n_thr]
+  uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_thr + n_thr);  // [2][n_thr + 1]
+  for (int i = threadIdx.x; i < n_thr; i += blockDim.x) s_thr[i] = thr[i];
+  for (int i = threadIdx.x; i < 2 * (n_thr + 1); i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
+  const int64_t total = n_pos + n_neg;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const bool is_neg = i >= n_pos;
+    const double x = static_cast<double>(is_neg ? neg[i - n_pos] : pos[i]);
+    int lo = 0, hi = n_thr;  // number of thresholds t with x >= t (thresholds ascending)
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (x >= s_thr[mid]) lo = mid + 1; else hi = mid;
+    }
+    atomicAdd(&s_hist[(is_neg ? n_thr + 1 : 0) + lo], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * (n_thr + 1); i += blockDim.x)
+    if (s_hist[i]) atomicAdd(&hist[i], static_cast<unsigned long long>(s_hist[i]));
+}
+
+__global__ void sweep_suffix_kernel(const unsigned long long* __restrict__ hist, int32_t n_thr,
+                                    int64_t* __restrict__ out) {
+  // one thread per class (pos / neg): counts[t] = sum_{b > t} hist[b]
+  const int c = threadIdx.x;
+  if (c >= 2) return;
+  const unsigned long long* h = hist + c * (n_thr + 1);
+  unsigned long long run = 0;
+  for (int t = n_thr - 1; t >= 0; --t) {
+    run += h[t + 1];
+    out[2 * t + c] = static_cast<int64_t>(run);
+  }
+}
+
+cudaError_t launch_threshold_sweep(const float* pos, int64_t n_pos, const float* neg, int64_t n_neg,
+                                   const double* thr, int32_t n_thr, int64_t* out_counts,
+                                   unsigned long long* hist_ws, int sm_count, cudaStream_t stream) {
+  if (n_thr < 1 || n_thr > kSweepMaxT) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemsetAsync(hist_ws, 0, sizeof(unsigned long long) * 2 * (n_thr + 1), stream);
+  if (e != cudaSuccess) return e;
+  const size_t smem = sizeof(double) * n_thr + sizeof(uint32_t) * 2 * (n_thr + 1);
+  const int64_t total = n_pos + n_neg;
+  int64_t grid = (total + 256 * 8 - 1) / (256 * 8);
+  if (grid > sm_count * 4) grid = sm_count * 4;
+  if (grid < 1) grid = 1;
+  e = cudaFuncSetAttribute(sweep_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           static_cast<int>(sizeof(double) * kSweepMaxT + sizeof(uint32_t) * 2 * (kSweepMaxT + 1)));
+  if (e != cudaSuccess) return e;
+  sweep_hist_kernel<<<static_cast<int>(grid), 256, smem, stream>>>(pos, n_pos, neg, n_neg, thr, n_thr, hist_ws);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  sweep_suffix_kernel<<<1, 32, 0, stream>>>(hist_ws, n_thr, out_counts);
+  return cudaGetLastError();
+}
+
+}  // namespace mmrs

@@ -1,0 +1,228 @@
+"""Near-duplicate join behind the reference's data-governance signatures.
+
+Reference tools (paths relative to the reference checkout):
+    tool/find_repeated.py                  cross-folder exact join (MD5 of RGB bytes), :35-71
+    tool/find_repeated_in_same_folder.py   same-folder near join (pHash/dHash/wHash, Hamming), :56-106
+    tool/delete repeated.py                train-vs-test join (dHash), :11-162
+BASELINE.json replaces the hash predicates by `cos(e_i, e_j) >= tau` on unit-norm embeddings
+(SURVEY.md M2); the call signatures and result tuples are kept.
+"""
+from __future__ import annotations
+
+import os
+from typing import Callable, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .gallery import DeviceGallery, _pad_dim
+from .search import search_topk, _stream_handle
+
+
+# ---- tensor level -------------------------------------------------------------------------------
+def _device_f32(emb, device=None) -> torch.Tensor:
+    if isinstance(emb, DeviceGallery):
+        if emb.mode != "fp32":
+            raise ValueError("exact self-join needs an fp32 gallery")
+        return emb.data
+    if isinstance(emb, np.ndarray):
+        emb = torch.from_numpy(emb)
+    if emb.dim() != 2:
+        raise ValueError("embeddings must be [N, D]")
+    dev = torch.device(device) if device is not None else (
+        emb.device if emb.is_cuda else torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0))
+    _cabi.require_b200(dev.index or 0)
+    n, d = emb.shape
+    dp = _pad_dim(d)
+    x = emb.detach().to(device=dev, dtype=torch.float32)
+    if dp != d:
+        x = torch.nn.functional.pad(x, (0, dp - d))
+    return x.contiguous()
+
+
+def selfjoin_raw(x: torch.Tensor, threshold: float, row_begin: int = 0, row_end: Optional[int] = None,
+                 capacity: Optional[int] = None) -> torch.Tensor:
+    """Unsorted int64 [P, 2] pairs (i < j, row_begin <= i < row_end) from the CUDA kernel;
+    grows the pair buffer and retries when the kernel reports more pairs than `capacity`."""
+    n = int(x.shape[0])
+    row_end = n if row_end is None else int(row_end)
+    lib = _cabi.lib
+    cap = int(capacity) if capacity is not None else max(4096, 2 * (row_end - row_begin))
+    with torch.cuda.device(x.device):
+        count = torch.zeros(1, dtype=torch.int64, device=x.device)
+        ws = torch.empty(512, dtype=torch.uint8, device=x.device)
+        while True:
+            pairs = torch.empty((cap, 2), dtype=torch.int64, device=x.device)
+            st = lib.mmrs_selfjoin_pairs(x.data_ptr(), n, int(x.shape[1]), x.stride(0), _cabi.DTYPE_F32,
+                                         float(threshold), int(row_begin), row_end, pairs.data_ptr(),
+                                         cap, count.data_ptr(), DeviceGallery.aligned_ptr(ws), 256,
+                                         _stream_handle(x.device))
+            found = int(count.item())
+            if st == _cabi.ERR_CAPACITY:
+                cap = found  # exact size is known now
+                continue
+            _cabi.check(st)
+            return pairs[:found]
+
+
+def sort_pairs(pairs: torch.Tensor, n: int) -> torch.Tensor:
+    """Lexicographic (i, j) order -- what `triu(S >= tau, 1).nonzero()` yields row-major."""
+    if pairs.numel() == 0:
+        return pairs.reshape(0, 2)
+    key = pairs[:, 0] * int(n) + pairs[:, 1]
+    return pairs[torch.argsort(key)].contiguous()
+
+
+def find_duplicate_pairs(emb, threshold: float, *, device=None) -> torch.Tensor:
+    """All (i, j), i < j, with <e_i, e_j> >= threshold over unit-norm fp32 rows -> int64 [P, 2]
+    sorted lexicographically.  Host input gives a host result."""
+    on_host = not isinstance(emb, DeviceGallery) and not (isinstance(emb, torch.Tensor) and emb.is_cuda)
+    x = _device_f32(emb, device)
+    pairs = sort_pairs(selfjoin_raw(x, threshold), int(x.shape[0]))
+    return pairs.cpu() if on_host else pairs
+
+
+def greedy_first_keeper(n: int, pairs, order: Sequence[int]):
+    """The keep/delete decision of tool/find_repeated_in_same_folder.py:76-95 on a pair list:
+    walk items in `order`; an item adjacent to an already kept representative is a duplicate of
+    the EARLIEST-kept such representative (the reference's `for ... break` over
+    reference_hashes), otherwise it becomes a representative.
+    Returns (representatives, [(dup, original)]) as item ids."""
+    pairs = np.asarray(pairs.cpu() if isinstance(pairs, torch.Tensor) else pairs, dtype=np.int64).reshape(-1, 2)
+    # CSR adjacency of the undirected pair graph
+    src = np.concatenate([pairs[:, 0], pairs[:, 1]])
+    dst = np.concatenate([pairs[:, 1], pairs[:, 0]])
+    o = np.argsort(src, kind="stable")
+    src, dst = src[o], dst[o]
+    start = np.searchsorted(src, np.arange(n + 1))
+    keep_rank = np.full(n, -1, dtype=np.int64)   # position in the representative list, -1 = not kept
+    reps, dups = [], []
+    for item in order:
+        nb = dst[start[item]:start[item + 1]]
+        ranks = keep_rank[nb]
+        ranks = ranks[ranks >= 0]
+        if ranks.size:
+            dups.append((int(item), reps[int(ranks.min())]))
+        else:
+            keep_rank[item] = len(reps)
+            reps.append(int(item))
+    return reps, dups
+
+
+# ---- file level -------------------------------------------------------------------------------
+IMAGE_EXTENSIONS = {'.jpg', '.jpeg', '.png', '.bmp', '.gif', '.tiff'}
+
+
+def get_all_images(folder_path):
+    """Drop-in for tool/find_repeated.py:21-33: recursive listing filtered by extension."""
+    image_files = []
+    for root, _, files in os.walk(folder_path):
+        image_files.extend(os.path.join(root, f) for f in files
+                           if os.path.splitext(f)[1].lower() in IMAGE_EXTENSIONS)
+    return image_files
+
+
+def pixel_embedding(paths: Sequence[str], size: int = 16):
+    """Default embedder when no CLIP encoder is supplied (the encoders are third-party and out of
+    scope): RGB pixels box-resized to size x size, mean-removed, unit-normalised.
+    Pixel-identical images (the MD5 predicate of find_repeated.py:6-19) map to identical vectors.
+    Returns (embeddings [n_ok, 3*size*size] fp32, ok_mask [len(paths)] bool); unreadable files
+    are reported and skipped like the reference does (:17-19)."""
+    from PIL import Image
+    vecs, ok = [], []
+    for p in paths:
+        try:
+            with Image.open(p) as img:
+                a = np.asarray(img.convert("RGB").resize((size, size), Image.BOX), dtype=np.float32).reshape(-1)
+            a = a - a.mean()
+            nrm = np.linalg.norm(a)
+            vecs.append(a / nrm if nrm > 0 else np.full_like(a, 1.0 / np.sqrt(a.size)))
+            ok.append(True)
+        except Exception as e:  # noqa: BLE001 -- mirror the reference's blanket handler
+            print(f"Error processing {p}: {e}")
+            ok.append(False)
+    emb = torch.from_numpy(np.stack(vecs)) if vecs else torch.empty((0, 3 * size * size))
+    return emb, np.array(ok, dtype=bool)
+
+
+Embedder = Callable[[Sequence[str]], "tuple[torch.Tensor, np.ndarray]"]
+
+
+def _remove(path: str, dry_run: bool) -> bool:
+    if dry_run:
+        return True
+    try:
+        os.remove(path)
+        return True
+    except Exception as e:  # noqa: BLE001
+        print(f"Failed to delete {path}: {e}")
+        return False
+
+
+def _cross_folder(reference_folder, delete_folder, embed: Embedder, threshold: float, dry_run: bool):
+    reference_images = get_all_images(reference_folder)
+    delete_images = get_all_images(delete_folder)
+    print(f"Found {len(reference_images)} images in reference folder")
+    print(f"Found {len(delete_images)} images in delete folder")
+    deleted_files, kept_files = [], []
+    ref_emb, ref_ok = embed(reference_images)
+    del_emb, del_ok = embed(delete_images)
+    ref_paths = [p for p, ok in zip(reference_images, ref_ok) if ok]
+    match = {}
+    if len(ref_paths) and del_emb.shape[0]:
+        # probe side = queries, build side = gallery: top-1 per delete image, thresholded
+        vals, idx = search_topk(del_emb, DeviceGallery(ref_emb, mode="fp32"), 1,
+                                normalize_queries=False, scale=1.0)
+        vals, idx = vals.cpu().numpy()[:, 0], idx.cpu().numpy()[:, 0]
+        ok_pos = np.flatnonzero(del_ok)
+        for row, (v, i) in enumerate(zip(vals, idx)):
+            if v >= threshold:
+                match[delete_images[ok_pos[row]]] = ref_paths[int(i)]
+    for img_path in delete_images:
+        if img_path in match:
+            if _remove(img_path, dry_run):
+                deleted_files.append((img_path, match[img_path]))
+        else:
+            kept_files.append(img_path)
+    return deleted_files, kept_files, len(reference_images), len(delete_images)
+
+
+def find_and_remove_near_duplicate_images(folder_path, similarity_threshold=0.95, *,
+                                          embed: Optional[Embedder] = None, dry_run: bool = False):
+    """Same-folder form, tool/find_repeated_in_same_folder.py:56-106: sort by file size descending
+    (:73), keep the first of every group of similar images, delete the rest.
+    Returns (deleted_files [(dup, original)], reference_images, total).
+    `similarity_threshold` is a cosine threshold here (the reference's is a Hamming radius)."""
+    embed = embed or pixel_embedding
+    all_images = get_all_images(folder_path)
+    print(f"在文件夹中找到 {len(all_images)} 个图像")
+    all_images.sort(key=lambda x: os.path.getsize(x), reverse=True)
+    emb, ok = embed(all_images)
+    usable = [p for p, good in zip(all_images, ok) if good]   # unreadable files are skipped (:78)
+    reference_images, duplicate_images = [], []
+    if len(usable) >= 2:
+        pairs = find_duplicate_pairs(emb, similarity_threshold)
+        reps, dups = greedy_first_keeper(len(usable), pairs, range(len(usable)))
+        reference_images = [usable[i] for i in reps]
+        duplicate_images = [(usable[d], usable[o]) for d, o in dups]
+    else:
+        reference_images = list(usable)
+    deleted_files = [(d, o) for d, o in duplicate_images if _remove(d, dry_run)]
+    return deleted_files, reference_images, len(all_images)
+
+
+def find_and_remove_duplicate_images(reference_folder, delete_folder=None, *, embed: Optional[Embedder] = None,
+                                     threshold: float = 0.9999, dry_run: bool = False):
+    """Drop-in for BOTH reference functions of this name.
+
+    (reference_folder, delete_folder: str)  -> tool/find_repeated.py:35-71
+        images of `delete_folder` that match an image of `reference_folder` are deleted;
+        returns (deleted_files [(path, ref_path)], kept_files, n_ref, n_del).
+    (folder_path, similarity_threshold: number | None) -> tool/find_repeated_in_same_folder.py:56-106
+        returns (deleted_files, reference_images, total).
+    """
+    if delete_folder is None or isinstance(delete_folder, (int, float)):
+        thr = 0.95 if delete_folder is None else float(delete_folder)
+        return find_and_remove_near_duplicate_images(reference_folder, thr, embed=embed, dry_run=dry_run)
+    return _cross_folder(reference_folder, delete_folder, embed or pixel_embedding, threshold, dry_run)

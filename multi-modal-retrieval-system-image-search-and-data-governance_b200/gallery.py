@@ -1,0 +1,113 @@
+"""Device-resident gallery.
+
+The reference keeps its gallery as a pickle `{relpath: float[D]}` (code/search_image.py:159-164),
+rebuilds an `np.array` -> `torch.tensor [N, D]` per class (`construct_dataset`, :167-182) and
+uploads the WHOLE matrix on every score call (`features.cuda()`, :107).  Here the matrix is
+uploaded once into HBM, row-major, rows 16-byte aligned (D padded with zeros to a multiple of 8),
+in fp32 (exact mode) or bf16 (tensor-core mode), and stays resident across calls.
+"""
+from __future__ import annotations
+
+import pickle
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _cabi
+
+
+def _pad_dim(d: int) -> int:
+    return (d + 7) // 8 * 8
+
+
+class DeviceGallery:
+    """[N, D] embedding matrix resident on one B200.
+
+    mode "fp32": values kept as given (exact mode: scores within 1e-5 of the torch CPU path).
+    mode "bf16": values rounded to bf16 -- that bf16 tensor IS the gallery.
+    `row_offset` is the global index of row 0 when this is one shard of a larger gallery.
+    """
+
+    def __init__(self, features, mode: Optional[str] = None, device: Optional[torch.device] = None,
+                 row_offset: int = 0, paths: Optional[Sequence[str]] = None):
+        if isinstance(features, np.ndarray):
+            features = torch.from_numpy(features)
+        if not isinstance(features, torch.Tensor) or features.dim() != 2:
+            raise TypeError("features must be a 2-D torch.Tensor / numpy array [N, D]")
+        if mode is None:
+            mode = "bf16" if features.dtype == torch.bfloat16 else "fp32"
+        if mode not in ("fp32", "bf16"):
+            raise ValueError("mode must be 'fp32' or 'bf16'")
+        if device is None:
+            device = features.device if features.is_cuda else torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0)
+        device = torch.device(device)
+        _cabi.require_b200(device.index if device.index is not None else 0)
+        self.mode = mode
+        self.device = device
+        self.n_rows, self.dim = int(features.shape[0]), int(features.shape[1])
+        if self.n_rows < 1 or self.dim < 1:
+            raise ValueError("gallery must have at least one row and one column")
+        self.row_offset = int(row_offset)
+        self.paths = list(paths) if paths is not None else None
+        dt = torch.bfloat16 if mode == "bf16" else torch.float32
+        dp = _pad_dim(self.dim)
+        src = features.detach()
+        if src.is_cuda and src.dtype == dt and dp == self.dim and src.is_contiguous():
+            data = src  # adopt in place (no copy): e.g. a shard generated on the device
+        else:
+            data = torch.zeros((self.n_rows, dp), dtype=dt, device=device)
+            # chunked upload keeps the pinned/pageable staging small for multi-GB galleries
+            step = max(1, (256 << 20) // max(1, self.dim * 4))
+            for lo in range(0, self.n_rows, step):
+                blk = src[lo:lo + step]
+                data[lo:lo + step, :self.dim] = blk.to(device=device, dtype=dt, non_blocking=False)
+        self.data = data
+        self.padded_dim = dp
+        self._workspaces: dict = {}
+
+    # -- C-ABI views ---------------------------------------------------------------------------
+    @property
+    def dtype_code(self) -> int:
+        return _cabi.DTYPE_BF16 if self.mode == "bf16" else _cabi.DTYPE_F32
+
+    @property
+    def nbytes(self) -> int:
+        return self.data.numel() * self.data.element_size()
+
+    def workspace(self, key, nbytes: int) -> torch.Tensor:
+        """Cached device scratch buffer (256-byte aligned) for repeated calls of one shape."""
+        buf = self._workspaces.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(int(nbytes), 256) + 256, dtype=torch.uint8, device=self.device)
+            self._workspaces[key] = buf
+        return buf
+
+    @staticmethod
+    def aligned_ptr(buf: torch.Tensor) -> int:
+        p = buf.data_ptr()
+        return (p + 255) // 256 * 256
+
+    def __len__(self) -> int:
+        return self.n_rows
+
+    def __repr__(self) -> str:
+        return (f"DeviceGallery(rows={self.n_rows}, dim={self.dim}, mode={self.mode}, "
+                f"device={self.device}, row_offset={self.row_offset})")
+
+
+def load_feature_cache(path: str):
+    """Read the reference's on-disk gallery formats.
+
+    *.pkl : pickle `{relpath: np.ndarray[D]}` written by build_cache (code/search_image.py:159-160)
+            -> (features [N, D] fp32 tensor, [relpath]) in the dict's insertion order
+    *.pt  : `torch.save` of an [N, D] tensor (pre_load_features, code/utils.py:150-151) -> (tensor, None)
+    """
+    if path.endswith(".pt"):
+        t = torch.load(path, map_location="cpu")
+        return t.to(torch.float32), None
+    with open(path, "rb") as f:
+        d = pickle.load(f)
+    keys = list(d.keys())
+    feats = torch.from_numpy(np.stack([np.asarray(d[k], dtype=np.float32).reshape(-1) for k in keys]))
+    return feats, keys

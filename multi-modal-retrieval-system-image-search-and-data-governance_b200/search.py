@@ -1,0 +1,274 @@
+"""Search hot path: the reference's scoring functions on top of the CUDA library.
+
+Mirrors (same names, positional order, return tuples) of code/search_image.py:
+    get_similarity   :105-117     construct_dataset :167-182
+    eval_threshold   :39-56       find_thresholds   :58-103
+and the tensor-level calls they sit on (`search_topk` returns like
+`output.topk(k, 1, True, True)`, code/utils.py:17).
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional, Union
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .gallery import DeviceGallery, _pad_dim
+
+# module-level configuration with the reference's names (code/search_image.py:14-38); scripts
+# that `from search_image import *` and set these keep working
+class_names = ["T-shirt", "badminton-racket", "baozi", "guitar", "lychee", "cherry", "tennis-racket",
+               "violin", "mantou", "dress-shirt"]
+class_to_idx = {name: i for i, name in enumerate(class_names)}
+dataset_path = "data/search"
+
+GalleryLike = Union[DeviceGallery, torch.Tensor, np.ndarray]
+
+
+def _as_gallery(gallery: GalleryLike, mode: Optional[str]) -> DeviceGallery:
+    if isinstance(gallery, DeviceGallery):
+        if mode is not None and mode != gallery.mode:
+            raise ValueError(f"gallery is resident in {gallery.mode} mode, asked for {mode}")
+        return gallery
+    return DeviceGallery(gallery, mode=mode)
+
+
+def _stream_handle(device: torch.device) -> int:
+    return int(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _prep_queries(queries, gal: DeviceGallery):
+    """-> (fp32 contiguous [Q, padded_dim] tensor, on_host: bool)."""
+    if isinstance(queries, np.ndarray):
+        queries = torch.from_numpy(queries)
+    if queries.dim() == 1:
+        queries = queries.unsqueeze(0)
+    if queries.dim() != 2 or queries.shape[1] != gal.dim:
+        raise ValueError(f"queries must be [Q, {gal.dim}], got {tuple(queries.shape)}")
+    q = queries.detach()
+    if q.dtype != torch.float32:
+        q = q.to(torch.float32)
+    if gal.padded_dim != gal.dim:
+        q = torch.nn.functional.pad(q, (0, gal.padded_dim - gal.dim))
+    if not q.is_contiguous():
+        q = q.contiguous()
+    if q.is_cuda and q.device != gal.device:
+        q = q.to(gal.device)
+    return q, not q.is_cuda
+
+
+def search_topk(queries, gallery: GalleryLike, k: int, *, normalize_queries: bool = True,
+                scale: float = 1.0, mode: Optional[str] = None, path: str = "auto"):
+    """Per-query top-k of `scale * q @ G.T` without materialising the score matrix.
+
+    Returns `(values [Q, k] fp32 descending, indices [Q, k] int64)` exactly like
+    `torch.topk(k, dim=1, largest=True, sorted=True)` (code/utils.py:17); equal scores are ordered
+    by ascending row index; indices are global (`gallery.row_offset` added).
+    Host queries (CPU tensor / numpy) give host results -- the reference's call shape
+    (host in, `.cpu()` out, code/search_image.py:105-109) -- device queries give device results.
+    """
+    gal = _as_gallery(gallery, mode)
+    q, on_host = _prep_queries(queries, gal)
+    nq = int(q.shape[0])
+    k = int(k)
+    if k < 1:
+        raise ValueError("k must be >= 1")
+    if k > gal.n_rows:
+        raise RuntimeError("selected index k out of range")  # torch.topk's message
+    lib = _cabi.lib
+    with torch.cuda.device(gal.device):
+        ws_bytes = lib.mmrs_search_workspace_bytes(gal.n_rows, gal.padded_dim, gal.dtype_code, max(nq, 1), k)
+        if on_host:
+            ws_bytes += lib.mmrs_search_host_staging_bytes(gal.padded_dim, max(nq, 1), k)
+            ws = gal.workspace(("search", nq, k, True), ws_bytes)
+            if nq > 0 and not q.is_pinned():
+                q = q.pin_memory()
+            values = torch.empty((nq, k), dtype=torch.float32, pin_memory=True)
+            indices = torch.empty((nq, k), dtype=torch.int64, pin_memory=True)
+            fn = lib.mmrs_search_topk_host
+        else:
+            ws = gal.workspace(("search", nq, k, False), ws_bytes)
+            values = torch.empty((nq, k), dtype=torch.float32, device=gal.device)
+            indices = torch.empty((nq, k), dtype=torch.int64, device=gal.device)
+            fn = lib.mmrs_search_topk
+        if nq == 0:
+            return values, indices
+        _cabi.check(fn(gal.data.data_ptr(), gal.n_rows, gal.padded_dim, gal.data.stride(0),
+                       gal.dtype_code, q.data_ptr(), nq, q.stride(0), k, int(bool(normalize_queries)),
+                       float(scale), gal.row_offset, _cabi.PATHS[path], values.data_ptr(),
+                       indices.data_ptr(), DeviceGallery.aligned_ptr(ws), ws_bytes,
+                       _stream_handle(gal.device)))
+    return values, indices
+
+
+def full_scores(queries, gallery: GalleryLike, *, normalize_queries: bool = True, scale: float = 1.0,
+                mode: Optional[str] = None, path: str = "auto") -> torch.Tensor:
+    """[Q, N] fp32 scores `scale * q @ G.T` (the expression of code/search_image.py:107,
+    CLIP/lab3.py:114 for all classes at once).  Host queries give a host result."""
+    gal = _as_gallery(gallery, mode)
+    q, on_host = _prep_queries(queries, gal)
+    nq = int(q.shape[0])
+    lib = _cabi.lib
+    with torch.cuda.device(gal.device):
+        if on_host:
+            q = q.to(gal.device)
+        out = torch.empty((nq, gal.n_rows), dtype=torch.float32, device=gal.device)
+        if nq > 0:
+            ws_bytes = lib.mmrs_full_scores_workspace_bytes(gal.n_rows, gal.padded_dim, gal.dtype_code, nq)
+            ws = gal.workspace(("scores", nq), ws_bytes)
+            _cabi.check(lib.mmrs_full_scores(gal.data.data_ptr(), gal.n_rows, gal.padded_dim,
+                                             gal.data.stride(0), gal.dtype_code, q.data_ptr(), nq,
+                                             q.stride(0), int(bool(normalize_queries)), float(scale),
+                                             _cabi.PATHS[path], out.data_ptr(), out.stride(0),
+                                             DeviceGallery.aligned_ptr(ws), ws_bytes,
+                                             _stream_handle(gal.device)))
+    return out.cpu() if on_host else out
+
+
+# one-entry upload cache: the reference re-uploads `features` on every call (:107); a script that
+# passes the same host tensor again (same storage, same version) reuses the resident copy
+_last_upload: dict = {}
+
+
+def _resident(features, mode: Optional[str]) -> DeviceGallery:
+    if isinstance(features, DeviceGallery):
+        return features
+    if isinstance(features, np.ndarray):
+        features = torch.from_numpy(features)
+    key = (features.data_ptr(), tuple(features.shape), features.dtype, features._version, mode)
+    hit = _last_upload.get("key")
+    if hit == key:
+        return _last_upload["gallery"]
+    gal = DeviceGallery(features, mode=mode)
+    _last_upload["key"] = key
+    _last_upload["gallery"] = gal
+    return gal
+
+
+def get_similarity(features, targets, label, ref_feature, device="cuda"):
+    """Drop-in for code/search_image.py:105-117.
+
+    `similarity = 100. * features.cuda() @ ref_feature.t()`; scores copied to host and split by
+    `targets == label` -> `(pos_res, neg_res)` numpy arrays.  `features` may be the host tensor
+    the reference passes (uploaded once, see _resident) or a DeviceGallery."""
+    del device  # the reference ignores its own argument too (hard-coded .cuda())
+    gal = _resident(features, None)
+    with torch.no_grad():
+        q = ref_feature if isinstance(ref_feature, torch.Tensor) else torch.as_tensor(ref_feature)
+        q = q.detach().reshape(1, -1).to(torch.float32)
+        if not q.is_cuda:
+            q = q.to(gal.device)
+        scores = full_scores(q, gal, normalize_queries=False, scale=100.0)[0].cpu().numpy()
+        targets = np.asarray(targets)
+        pos_mask = (targets == label)
+        neg_mask = (targets != label)
+        return scores[pos_mask], scores[neg_mask]
+
+
+def construct_dataset(feature_dict, sample_images, class_name):
+    """Drop-in for code/search_image.py:167-182: gallery of every cached image except the
+    `sample_images` of `class_name`; returns `(test_features [N, D] tensor, targets np.ndarray)`.
+    Uses this module's `class_names`, `class_to_idx`, `dataset_path` like the reference's globals."""
+    test_imgs = []
+    targets = []
+    for cls_name in class_names:
+        listing = os.listdir(os.path.join(dataset_path, cls_name))
+        if cls_name == class_name:
+            listing = [p for p in listing if p not in sample_images]
+        test_imgs.extend(cls_name + "/" + p for p in listing)
+        targets.extend([class_to_idx[cls_name]] * len(listing))
+    targets = np.array(targets)
+    test_features = torch.tensor(np.array([feature_dict[img] for img in test_imgs]))
+    return test_features, targets
+
+
+# ---- threshold sweep ---------------------------------------------------
+def threshold_sweep_counts(pos_res, neg_res, thresholds, device: Optional[torch.device] = None):
+    """(tp [T], fp [T]) int64 numpy: tp[t] = #{pos >= thresholds[t]}, fp likewise, on the GPU.
+    Thresholds must be ascending (np.linspace(min, max, T) is)."""
+    thr = np.ascontiguousarray(np.asarray(thresholds, dtype=np.float64).reshape(-1))
+    if thr.size > 1 and np.any(np.diff(thr) < 0):
+        raise ValueError("thresholds must be ascending")
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0)
+    _cabi.require_b200(dev.index or 0)
+
+    def dev_f32(x):
+        if isinstance(x, torch.Tensor):
+            return x.detach().to(device=dev, dtype=torch.float32).contiguous().reshape(-1)
+        return torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float32).reshape(-1))).to(dev)
+
+    with torch.cuda.device(dev):
+        p, n = dev_f32(pos_res), dev_f32(neg_res)
+        t = torch.from_numpy(thr).to(dev)
+        out = torch.empty((thr.size, 2), dtype=torch.int64, device=dev)
+        ws_bytes = _cabi.lib.mmrs_threshold_sweep_workspace_bytes(thr.size)
+        ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=dev)
+        _cabi.check(_cabi.lib.mmrs_threshold_sweep(p.data_ptr(), p.numel(), n.data_ptr(), n.numel(),
+                                                   t.data_ptr(), thr.size, out.data_ptr(),
+                                                   DeviceGallery.aligned_ptr(ws), ws_bytes,
+                                                   _stream_handle(dev)))
+        counts = out.cpu().numpy()
+    return counts[:, 0].copy(), counts[:, 1].copy()
+
+
+def _f1_from_counts(tp, fp, n_pos):
+    # the reference's arithmetic (code/search_image.py:43-54): numpy int64 counts, float64 ratios,
+    # 0/0 -> nan exactly as there
+    fn = n_pos - tp
+    with np.errstate(divide="ignore", invalid="ignore"):
+        precision = tp / (tp + fp)
+        recall = tp / (tp + fn)
+        f1 = 2 * precision * recall / (precision + recall)
+    return f1, precision, recall
+
+
+def eval_threshold(pos_res, neg_res, threshold):
+    """Drop-in for code/search_image.py:39-56 -> (f1_score, precision, recall)."""
+    tp, fp = threshold_sweep_counts(pos_res, neg_res, [threshold])
+    f1, p, r = _f1_from_counts(tp, fp, int(np.asarray(pos_res).size))
+    return f1[0], p[0], r[0]
+
+
+def find_thresholds(pos_res, neg_res, target_class, verbose=False):
+    """Drop-in for code/search_image.py:58-103: 200-point linspace over [min, max] of all scores,
+    F1 per threshold, FIRST strict maximum wins (:74); returns best_f1_score.  The O(200 * N)
+    interpreted `sum(pos_res >= threshold)` loops run as one histogram pass on the GPU."""
+    pos_np = np.asarray(pos_res)
+    neg_np = np.asarray(neg_res)
+    min_val = min(pos_np.min(), neg_np.min())
+    max_val = max(pos_np.max(), neg_np.max())
+    thresholds = np.linspace(min_val, max_val, 200)
+    tp, fp = threshold_sweep_counts(pos_np, neg_np, thresholds)
+    f1s, ps, rs = _f1_from_counts(tp, fp, int(pos_np.size))
+
+    best_threshold = 0.
+    best_f1_score = 0.
+    best_precision = 0.
+    best_recall = 0.
+    for t, f1, p, r in zip(thresholds, f1s, ps, rs):
+        if f1 > best_f1_score:
+            best_threshold, best_f1_score, best_precision, best_recall = t, f1, p, r
+
+    if verbose:
+        print(f"{target_class}_best_threshold", best_threshold)
+        print(f"{target_class}_best_f1_score", best_f1_score)
+        print(f"{target_class}_best_precision", best_precision)
+        print(f"{target_class}_best_recall", best_recall)
+        try:  # the reference plots the curve (:81-100); matplotlib is optional here
+            import matplotlib
+            matplotlib.use("Agg")
+            import matplotlib.pyplot as plt
+            plt.figure(figsize=(9, 9))
+            plt.plot(thresholds, f1s)
+            plt.scatter(x=best_threshold, y=best_f1_score)
+            plt.annotate(f"threshold:{best_threshold:.5f}/f1:{best_f1_score:.5f}", xy=(best_threshold, best_f1_score))
+            plt.xlabel('threshold')
+            plt.ylabel('f1_score')
+            plt.title(f'{target_class}_precision:{best_precision:.4f}_recall:{best_recall:.4f}')
+            plt.savefig(f'result_{target_class}_all.jpg')
+        except ImportError:
+            print("(matplotlib not installed: F1 curve not plotted)")
+        print('done')
+    return best_f1_score

@@ -1,0 +1,148 @@
+"""Row-sharded gallery over the GPUs of one box.
+
+One process per GPU (`torch.distributed`, backend "nccl" over NVLink 5 / NVSwitch).  The gallery is
+split into contiguous row blocks, queries are replicated, every rank runs the fused local top-k
+on its shard with global row ids, ONE all-gather moves the `[Q, k]` (value, index) lists --
+Q*k*12 bytes per rank -- and every rank merges the `world * k` candidates per query with the same
+order rule (score desc, index asc).  There is no other exchange: the scan itself is embarrassingly
+parallel, so scaling is weak in the gallery and the collective is latency-sized.
+
+The reference has no distributed code at all; this is new.
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _cabi
+from .gallery import DeviceGallery
+
+
+def shard_bounds(n_rows: int, world: int, align: int = 128) -> list[tuple[int, int]]:
+    """Contiguous [lo, hi) row blocks, one per rank, block starts aligned to the 128-row tile
+    (global index = lo + local index).  Earlier ranks hold lower indices, so "lower rank first"
+    agrees with the index-ascending tie rule."""
+    if world < 1:
+        raise ValueError("world must be >= 1")
+    per = math.ceil(n_rows / world / align) * align if n_rows > 0 else 0
+    out = []
+    for r in range(world):
+        lo = min(n_rows, r * per)
+        hi = min(n_rows, lo + per)
+        out.append((lo, hi))
+    return out
+
+
+def triangle_bounds(n_rows: int, world: int, align: int = 128) -> list[tuple[int, int]]:
+    """Row ranges of the i-side of the upper-triangular self-join with equal PAIR counts:
+    rows [lo, hi) own pairs (i, j > i), i.e. area ~ integral of (n - i); boundary r solves
+    1 - (1 - x)^2 = r / world."""
+    bounds = [0]
+    for r in range(1, world):
+        x = 1.0 - math.sqrt(1.0 - r / world)
+        b = int(round(x * n_rows / align)) * align
+        bounds.append(min(max(b, bounds[-1]), n_rows))
+    bounds.append(n_rows)
+    return [(bounds[i], bounds[i + 1]) for i in range(world)]
+
+
+def _all_gather(t: torch.Tensor, world: int, group) -> torch.Tensor:
+    """[world, *t.shape] gathered copy of `t` (same shape on every rank); one collective."""
+    t = t.contiguous()
+    out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+    if t.numel():
+        dist.all_gather_into_tensor(out.view(-1), t.view(-1), group=group)
+    return out
+
+
+def _merge_cuda(values: torch.Tensor, indices: torch.Tensor, k: int):
+    """values/indices [G, Q, k_in] on one device -> merged (values [Q, k], indices [Q, k])."""
+    g, q, kin = values.shape
+    dev = values.device
+    lib = _cabi.lib
+    out_v = torch.empty((q, k), dtype=torch.float32, device=dev)
+    out_i = torch.empty((q, k), dtype=torch.int64, device=dev)
+    if q == 0:
+        return out_v, out_i
+    with torch.cuda.device(dev):
+        ws_bytes = lib.mmrs_topk_merge_workspace_bytes(g, q, kin)
+        ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=dev)
+        _cabi.check(lib.mmrs_topk_merge(values.contiguous().data_ptr(), indices.contiguous().data_ptr(),
+                                        g, q, kin, k, out_v.data_ptr(), out_i.data_ptr(),
+                                        DeviceGallery.aligned_ptr(ws), ws_bytes,
+                                        int(torch.cuda.current_stream(dev).cuda_stream)))
+    return out_v, out_i
+
+
+class ShardedGallery:
+    """This rank's shard of a row-sharded gallery plus the merge step.
+
+    `local` is the rank's DeviceGallery with `row_offset` = first global row.  `local_search` and
+    `merge` exist so the host-side protocol (gather layout, index offsets, tie rule) can be
+    exercised on CPU with the gloo backend in tests; the product defaults are the CUDA kernels.
+    """
+
+    def __init__(self, local, n_rows_global: int, group: Optional[dist.ProcessGroup] = None,
+                 local_search: Optional[Callable] = None, merge: Optional[Callable] = None):
+        self.local = local
+        self.n_rows_global = int(n_rows_global)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if local_search is None:
+            from .search import search_topk as local_search
+        self._search = local_search
+        self._merge = merge or _merge_cuda
+
+    @classmethod
+    def from_full(cls, features: torch.Tensor, mode: Optional[str] = None, device=None,
+                  group: Optional[dist.ProcessGroup] = None) -> "ShardedGallery":
+        """Every rank is handed the full host matrix and keeps only its block."""
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        lo, hi = shard_bounds(features.shape[0], world)[rank]
+        local = DeviceGallery(features[lo:hi], mode=mode, device=device, row_offset=lo)
+        return cls(local, features.shape[0], group)
+
+    def search_topk(self, queries: torch.Tensor, k: int, *, normalize_queries: bool = True,
+                    scale: float = 1.0, path: str = "auto"):
+        """Global top-k, identical on every rank.  `queries` must be the same on all ranks."""
+        n_local = len(self.local)
+        k_local = min(k, n_local)
+        if k > self.n_rows_global:
+            raise RuntimeError("selected index k out of range")
+        v, i = self._search(queries, self.local, k_local, normalize_queries=normalize_queries,
+                            scale=scale, path=path)
+        if self.world == 1:
+            return v, i
+        if k_local < k:
+            # a shard smaller than k: pad with -inf / sentinel so all ranks gather equal shapes
+            pad = k - k_local
+            v = torch.cat([v, torch.full((v.shape[0], pad), float("-inf"), dtype=v.dtype, device=v.device)], 1)
+            i = torch.cat([i, torch.full((i.shape[0], pad), 2 ** 32 - 1, dtype=i.dtype, device=i.device)], 1)
+        gv = _all_gather(v, self.world, self.group)
+        gi = _all_gather(i, self.world, self.group)
+        return self._merge(gv, gi, k)
+
+    def find_duplicate_pairs(self, emb_full: torch.Tensor, threshold: float, raw_join: Optional[Callable] = None):
+        """Self-join with the gallery replicated (10M x 512 fp32 = 20 GB fits every GPU) and the
+        upper-triangular tile grid split by equal pair count; variable-length pair lists are
+        gathered (counts first, then padded buffers) and sorted lexicographically."""
+        from .dedup import selfjoin_raw, sort_pairs
+        raw_join = raw_join or selfjoin_raw
+        n = int(emb_full.shape[0])
+        lo, hi = triangle_bounds(n, self.world)[self.rank]
+        pairs = raw_join(emb_full, threshold, lo, hi) if hi > lo else emb_full.new_empty((0, 2), dtype=torch.int64)
+        if self.world == 1:
+            return sort_pairs(pairs, n)
+        cnt = torch.tensor([pairs.shape[0]], dtype=torch.int64, device=pairs.device)
+        cnts = _all_gather(cnt, self.world, self.group).view(-1)
+        m = int(cnts.max().item())
+        buf = torch.zeros((max(m, 1), 2), dtype=torch.int64, device=pairs.device)
+        buf[:pairs.shape[0]] = pairs
+        allbuf = _all_gather(buf, self.world, self.group)
+        parts = [allbuf[r, :int(cnts[r].item())] for r in range(self.world)]
+        return sort_pairs(torch.cat(parts, dim=0), n)

@@ -1,0 +1,71 @@
+"""Seeded inputs shared by make_golden.py (which feeds them to the reference's own functions)
+and by the tests (which feed the same inputs to the oracle and to the CUDA path)."""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+
+def similarity_inputs() -> dict:
+    """name -> (features [N, D] fp32 unit rows, targets [N] int, label, ref_feature [D]).
+
+    Mirrors what code/search_image.py:main feeds get_similarity: a unit-normalised gallery
+    (:157), integer class targets (:178), and a query that is a mean of unit vectors and hence
+    NOT unit norm (:310-318, :387)."""
+    out = {}
+    for name, (n, d, n_cls, seed) in {"small": (257, 64, 5, 11), "clip512": (2000, 512, 10, 1),
+                                      "taiyi768": (1001, 768, 6, 7)}.items():
+        g = torch.Generator().manual_seed(seed)
+        centers = torch.randn(n_cls, d, generator=g)
+        targets = torch.randint(0, n_cls, (n,), generator=g)
+        feats = centers[targets] * 0.6 + torch.randn(n, d, generator=g)
+        feats = feats / feats.norm(dim=-1, keepdim=True)
+        label = 2
+        members = feats[targets == label][:10]
+        text = centers[label] / centers[label].norm()
+        ref_feature = (members.mean(dim=0) + text) / 2      # search_image.py:387, un-normalised
+        out[name] = (feats.contiguous(), targets.numpy(), label, ref_feature.contiguous())
+    return out
+
+
+def topk_inputs() -> dict:
+    """name -> (logits [N, C] fp32, target [N] int64); includes rows with exact ties."""
+    g = torch.Generator().manual_seed(5)
+    logits = torch.randn(64, 6, generator=g)
+    target = torch.randint(0, 6, (64,), generator=g)
+    tied = torch.randn(32, 6, generator=g).round()   # many exact ties per row
+    tied_t = torch.randint(0, 6, (32,), generator=g)
+    return {"random": (logits, target), "tied": (tied, tied_t)}
+
+
+def dedup_image_set(root: str):
+    """Two folders of small generated images; some files of the delete folder are pixel-identical
+    to reference images (one saved in a different lossless format), one reference image is
+    duplicated inside the reference folder, one file is not an image."""
+    from PIL import Image
+    rng = np.random.default_rng(3)
+    ref_dir = os.path.join(root, "reference")
+    del_dir = os.path.join(root, "delete")
+    os.makedirs(os.path.join(ref_dir, "sub"))
+    os.makedirs(os.path.join(del_dir, "nested", "deep"))
+    imgs = [rng.integers(0, 256, size=(16 + i, 20, 3), dtype=np.uint8) for i in range(8)]
+
+    def save(arr, path):
+        Image.fromarray(arr, "RGB").save(path)
+
+    save(imgs[0], os.path.join(ref_dir, "a.png"))
+    save(imgs[1], os.path.join(ref_dir, "b.bmp"))
+    save(imgs[2], os.path.join(ref_dir, "sub", "c.png"))
+    save(imgs[2], os.path.join(ref_dir, "sub", "c_again.png"))   # same hash twice: last one wins (:52)
+    save(imgs[3], os.path.join(ref_dir, "d.tiff"))
+    save(imgs[0], os.path.join(del_dir, "a_copy.bmp"))            # dup of a.png, other container
+    save(imgs[2], os.path.join(del_dir, "nested", "c_copy.png"))
+    save(imgs[4], os.path.join(del_dir, "unique1.png"))
+    save(imgs[5], os.path.join(del_dir, "nested", "deep", "unique2.bmp"))
+    save(imgs[3], os.path.join(del_dir, "nested", "deep", "d_copy.png"))
+    save(imgs[6], os.path.join(del_dir, "skipped.webp"))          # extension not in the list (:26)
+    with open(os.path.join(del_dir, "broken.png"), "wb") as f:    # unreadable: hash None -> kept (:67-69)
+        f.write(b"not an image")
+    return ref_dir, del_dir

@@ -1,0 +1,106 @@
+"""Generate golden vectors by executing the REFERENCE'S OWN function bodies in this container.
+
+Run once here (the reference checkout is not present on the GPU box):
+    python tests/golden/make_golden.py [/root/reference]
+
+Nothing from the reference is copied into the repository: the functions are pulled out of the
+reference files with `ast` at generation time, compiled, and run on seeded synthetic inputs; only
+their inputs' seeds and their OUTPUTS are stored (tests/golden/*.npz, *.json).
+
+  code/search_image.py   get_similarity (:105-117), eval_threshold (:39-56), find_thresholds (:58-103)
+  code/utils.py          cls_acc (:15-39)  -> the only topk in the repo (:17)
+  tool/find_repeated.py  calculate_image_hash (:6-19), get_all_images (:21-33),
+                         find_and_remove_duplicate_images (:35-71)
+
+The one patch applied: torch.Tensor.cuda is made a no-op (this container has no GPU and
+search_image.py:107 hard-codes `.cuda()`), so the reference's arithmetic runs as its torch CPU
+fp32 path -- exactly the oracle BASELINE.json names.
+"""
+from __future__ import annotations
+
+import ast
+import json
+import os
+import sys
+import tempfile
+from pathlib import Path
+
+import numpy as np
+import torch
+
+HERE = Path(__file__).resolve().parent
+sys.path.insert(0, str(HERE))
+from golden_inputs import (dedup_image_set, similarity_inputs, topk_inputs)  # noqa: E402
+
+
+def extract_functions(path: Path, names: list[str], namespace: dict) -> dict:
+    tree = ast.parse(path.read_text(encoding="utf-8"))
+    picked = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    missing = set(names) - {n.name for n in picked}
+    if missing:
+        raise RuntimeError(f"{path}: functions not found: {missing}")
+    mod = ast.Module(body=picked, type_ignores=[])
+    exec(compile(mod, str(path), "exec"), namespace)
+    return namespace
+
+
+def main(ref_root: str) -> None:
+    ref = Path(ref_root)
+    torch.Tensor.cuda = lambda self, *a, **k: self  # the single patch (see module docstring)
+
+    # ---- search_image.py ------------------------------------------------------------------
+    ns = {"np": np, "torch": torch}
+    extract_functions(ref / "code" / "search_image.py",
+                      ["get_similarity", "eval_threshold", "find_thresholds"], ns)
+    out = {}
+    for name, (features, targets, label, ref_feature) in similarity_inputs().items():
+        pos, neg = ns["get_similarity"](features, targets, label, ref_feature)
+        out[f"{name}_pos"] = pos
+        out[f"{name}_neg"] = neg
+        probe = np.linspace(min(pos.min(), neg.min()), max(pos.max(), neg.max()), 7)
+        with np.errstate(all="ignore"):
+            ev = np.array([ns["eval_threshold"](pos, neg, t) for t in probe], dtype=np.float64)
+            best_f1 = ns["find_thresholds"](pos, neg, "golden", verbose=False)
+        out[f"{name}_probe"] = probe
+        out[f"{name}_eval"] = ev
+        out[f"{name}_best_f1"] = np.float64(best_f1)
+    np.savez(HERE / "search_image_golden.npz", **out)
+
+    # ---- utils.py cls_acc / topk ----------------------------------------------------------
+    ns2 = {"torch": torch}
+    extract_functions(ref / "code" / "utils.py", ["cls_acc"], ns2)
+    out2 = {}
+    for name, (logits, target) in topk_inputs().items():
+        for k in (1, 3):
+            out2[f"{name}_acc_k{k}"] = np.float64(ns2["cls_acc"](logits, target, topk=k))
+            v, i = logits.topk(k, 1, True, True)   # the expression at utils.py:17
+            out2[f"{name}_topk{k}_values"] = v.numpy()
+            out2[f"{name}_topk{k}_indices"] = i.numpy()
+    np.savez(HERE / "utils_topk_golden.npz", **out2)
+
+    # ---- tool/find_repeated.py --------------------------------------------------------------
+    import hashlib
+    from collections import defaultdict
+    from PIL import Image
+    ns3 = {"os": os, "hashlib": hashlib, "Image": Image, "defaultdict": defaultdict}
+    extract_functions(ref / "tool" / "find_repeated.py",
+                      ["calculate_image_hash", "get_all_images", "find_and_remove_duplicate_images"], ns3)
+    with tempfile.TemporaryDirectory() as tmp:
+        ref_dir, del_dir = dedup_image_set(tmp)
+        hashes = {os.path.relpath(p, tmp): ns3["calculate_image_hash"](p)
+                  for p in sorted(ns3["get_all_images"](tmp))}
+        deleted, kept, n_ref, n_del = ns3["find_and_remove_duplicate_images"](ref_dir, del_dir)
+        rel = lambda p: os.path.relpath(p, tmp)
+        golden = {
+            "hashes": hashes,
+            "deleted": sorted([rel(a), rel(b)] for a, b in deleted),
+            "kept": sorted(rel(p) for p in kept),
+            "n_ref": n_ref, "n_del": n_del,
+            "remaining_in_delete_folder": sorted(rel(p) for p in ns3["get_all_images"](del_dir)),
+        }
+    (HERE / "find_repeated_golden.json").write_text(json.dumps(golden, indent=1, sort_keys=True))
+    print("golden vectors written to", HERE)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1] if len(sys.argv) > 1 else "/root/reference")

@@ -1,0 +1,86 @@
+"""Parity of the CUDA self-join and the file-level dedup wrappers with the oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from golden_inputs import dedup_image_set
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n,d,frac", [(2, 8, 0.5), (300, 64, 0.1), (129, 16, 0.2), (5000, 512, 0.02), (20_000, 128, 0.01)])
+def test_pairs_bit_exact(mm, oracle, n, d, frac):
+    x, planted = oracle.synthetic_dedup(n, d, dup_frac=frac, seed=n)
+    want = oracle.dedup_pairs(x, 0.95)
+    got = mm.find_duplicate_pairs(x, 0.95)
+    assert got.dtype == torch.int64 and torch.equal(got, want)
+    assert [tuple(p) for p in got.tolist()] == planted
+
+
+def test_no_pairs_and_all_pairs(mm, oracle):
+    x = oracle.synthetic_gallery(500, 64, seed=1, dtype=torch.float32)
+    assert mm.find_duplicate_pairs(x, 0.95).shape == (0, 2)
+    got = mm.find_duplicate_pairs(x, -2.0)             # every pair qualifies: exercises buffer regrowth
+    assert got.shape[0] == 500 * 499 // 2 and torch.equal(got, oracle.dedup_pairs(x, -2.0))
+
+
+def test_row_ranges_partition_the_join(mm, oracle):
+    from mmrs_b200.dedup import selfjoin_raw, sort_pairs, _device_f32
+    from mmrs_b200.sharded import triangle_bounds
+    x, planted = oracle.synthetic_dedup(10_000, 64, dup_frac=0.03, seed=3)
+    xd = _device_f32(x)
+    parts = [selfjoin_raw(xd, 0.95, lo, hi) for lo, hi in triangle_bounds(10_000, 4)]
+    got = sort_pairs(torch.cat(parts), 10_000).cpu()
+    assert [tuple(p) for p in got.tolist()] == planted
+
+
+def test_same_folder_wrapper(mm, oracle, tmp_path):
+    dedup_image_set(str(tmp_path))
+    folder = str(tmp_path)
+    paths = mm.get_all_images(folder)
+    before = set(paths)
+    deleted, refs, total = mm.find_and_remove_duplicate_images(folder, 0.9999)
+    assert total == len(paths)
+    # oracle: same embedding, oracle pairs, oracle greedy walk in file-size order
+    from mmrs_b200.dedup import pixel_embedding
+    order_paths = sorted(paths, key=lambda p: os.path.getsize(p), reverse=True)
+    # (files were deleted; recompute the expectation from a fresh copy)
+    import shutil
+    fresh = tmp_path.parent / (tmp_path.name + "_fresh")
+    fresh.mkdir()
+    dedup_image_set(str(fresh))
+    fpaths = mm.get_all_images(str(fresh))
+    fpaths.sort(key=lambda p: os.path.getsize(p), reverse=True)
+    emb, ok = pixel_embedding(fpaths)
+    usable = [p for p, g in zip(fpaths, ok) if g]
+    pairs = oracle.dedup_pairs(emb, 0.9999)
+    reps, dups = oracle.greedy_keep_first(len(usable), pairs.tolist(), list(range(len(usable))))
+    rel = lambda p, root: os.path.relpath(p, root)
+    assert sorted(rel(p, folder) for p in refs) == sorted(rel(usable[r], fresh) for r in reps)
+    assert sorted((rel(a, folder), rel(b, folder)) for a, b in deleted) == \
+        sorted((rel(usable[d], fresh), rel(usable[o], fresh)) for d, o in dups)
+    assert len(deleted) == 4                                   # a_copy, c_again/c_copy (2 of 3), d_copy
+    assert set(mm.get_all_images(folder)) == before - {d for d, _ in deleted}
+    shutil.rmtree(fresh)
+
+
+def test_cross_folder_wrapper_matches_reference_golden(mm, tmp_path):
+    """With the pixel embedder the cosine predicate at 0.9999 reproduces the reference's MD5 join
+    on this image set, so the result tuple must equal the one recorded from find_repeated.py --
+    except which of two identical reference images is reported (hash dict: last wins; top-1: the
+    lower index wins) and unreadable files."""
+    gold = json.loads((GOLDEN / "find_repeated_golden.json").read_text())
+    ref_dir, del_dir = dedup_image_set(str(tmp_path))
+    rel = lambda p: os.path.relpath(p, tmp_path)
+    deleted, kept, n_ref, n_del = mm.find_and_remove_duplicate_images(ref_dir, del_dir)
+    assert (n_ref, n_del) == (gold["n_ref"], gold["n_del"])
+    assert sorted(rel(a) for a, _ in deleted) == sorted(a for a, _ in gold["deleted"])
+    assert sorted(rel(p) for p in kept) == gold["kept"]
+    for a, b in deleted:
+        want = dict(gold["deleted"])[rel(a)]
+        assert rel(b) == want or {rel(b), want} == {"reference/sub/c.png", "reference/sub/c_again.png"}
+    assert sorted(rel(p) for p in mm.get_all_images(del_dir)) == gold["remaining_in_delete_folder"]

@@ -1,0 +1,121 @@
+"""Host-side logic that needs no GPU: phase schedule, sharding arithmetic, greedy clustering,
+file listing, gallery-cache readers."""
+import ctypes
+import os
+import pickle
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+PKG = ROOT / "multi-modal-retrieval-system-image-search-and-data-governance_b200"
+
+
+@pytest.fixture(scope="module")
+def plan_lib(tmp_path_factory):
+    """plan.h compiled with g++ behind a tiny C shim."""
+    d = tmp_path_factory.mktemp("plan")
+    src = d / "shim.cpp"
+    src.write_text(f'''
+#include "{PKG / "csrc" / "plan.h"}"
+extern "C" int plan(long long n, int k, int ratio, int dense, int* out) {{
+  mmrs::SearchPlan p = mmrs::make_search_plan(n, k, 128, ratio, dense);
+  out[0] = p.n_tiles; out[1] = p.n_phases; out[2] = p.dense_rows; out[3] = p.cap;
+  for (int i = 0; i < p.n_phases; ++i) {{ out[4+3*i] = p.phase[i].inc; out[5+3*i] = p.phase[i].exc; out[6+3*i] = p.phase[i].n_sel; }}
+  return 0;
+}}''')
+    so = d / "shim.so"
+    subprocess.run(["g++", "-O1", "-shared", "-fPIC", str(src), "-o", str(so)], check=True)
+    return ctypes.CDLL(str(so))
+
+
+def get_plan(lib, n, k, ratio=4, dense=64):
+    out = (ctypes.c_int * 64)()
+    lib.plan(ctypes.c_longlong(n), k, ratio, dense, out)
+    phases = [(out[4 + 3 * i], out[5 + 3 * i], out[6 + 3 * i]) for i in range(out[1])]
+    return dict(n_tiles=out[0], dense_rows=out[2], cap=out[3], phases=phases)
+
+
+@pytest.mark.parametrize("n", [1, 127, 128, 129, 16384, 16385, 20000, 70000, 1_000_000, 12_500_000, 100_000_000])
+@pytest.mark.parametrize("k", [1, 10, 100, 1024])
+def test_plan_visits_every_tile_exactly_once(plan_lib, n, k):
+    p = get_plan(plan_lib, n, k)
+    T = p["n_tiles"]
+    assert T == (n + 127) // 128
+    seen = np.zeros(T, dtype=np.int32)
+    for inc, exc, n_sel in p["phases"]:
+        t = np.arange(n_sel, dtype=np.int64) * inc
+        assert t.max() < T and n_sel == (T + inc - 1) // inc
+        if exc:
+            t = t[t % exc != 0]
+        np.add.at(seen, t, 1)
+    assert (seen == 1).all()
+    # phase 0 is dense and unfiltered, holds >= k valid rows, and fits the list
+    inc0, exc0, n0 = p["phases"][0]
+    assert exc0 == 0 and p["dense_rows"] == n0 * 128 <= p["cap"]
+    valid0 = sum(min(128, n - j * inc0 * 128) for j in range(n0))
+    assert valid0 >= min(k, n)
+    # later phases: expected appends k * ratio stay far below the capacity
+    for (inc_prev, _, _), (inc, _, _) in zip(p["phases"], p["phases"][1:]):
+        assert inc_prev % inc == 0 and 4 * (k + 32) * (inc_prev // inc) <= p["cap"]
+
+
+def test_shard_bounds(mm):
+    for n, w in [(1_000_000, 8), (100_000_000, 8), (1000, 3), (5, 4), (128, 2), (129, 2)]:
+        b = mm.shard_bounds(n, w)
+        assert len(b) == w and b[0][0] == 0 and b[-1][1] == n
+        assert all(lo % 128 == 0 or lo == n for lo, _ in b)
+        assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+    from mmrs_b200.sharded import triangle_bounds
+    n = 1_000_000
+    tb = triangle_bounds(n, 8)
+    assert tb[0][0] == 0 and tb[-1][1] == n
+    areas = [sum(n - i for i in (lo, hi - 1)) * (hi - lo) / 2 for lo, hi in tb]
+    assert max(areas) / min(areas) < 1.02      # equal pair counts per rank
+
+
+def test_greedy_first_keeper_matches_oracle(mm, oracle):
+    rng = np.random.default_rng(0)
+    for n, m in [(10, 12), (200, 300), (1000, 5000)]:
+        pairs = rng.integers(0, n, size=(m, 2))
+        pairs = np.unique(np.sort(pairs[pairs[:, 0] != pairs[:, 1]], axis=1), axis=0)
+        order = rng.permutation(n).tolist()
+        assert mm.greedy_first_keeper(n, pairs, order) == oracle.greedy_keep_first(n, pairs.tolist(), order)
+
+
+def test_get_all_images_matches_oracle(mm, oracle, tmp_path):
+    from golden_inputs import dedup_image_set
+    dedup_image_set(str(tmp_path))
+    assert mm.get_all_images(str(tmp_path)) == oracle.get_all_images(str(tmp_path))
+    assert not any(p.endswith(".webp") for p in mm.get_all_images(str(tmp_path)))
+
+
+def test_load_feature_cache(mm, tmp_path):
+    d = {f"cls/{i}.jpg": np.random.default_rng(i).standard_normal(16).astype(np.float16) for i in range(5)}
+    with open(tmp_path / "features.pkl", "wb") as f:
+        pickle.dump(d, f)                              # the format of search_image.py:159-160
+    feats, keys = mm.load_feature_cache(str(tmp_path / "features.pkl"))
+    assert keys == list(d) and feats.shape == (5, 16) and feats.dtype == torch.float32
+    np.testing.assert_array_equal(feats.numpy(), np.stack([d[k] for k in keys]).astype(np.float32))
+    torch.save(torch.randn(7, 16), tmp_path / "test_f.pt")   # utils.py:150
+    feats, keys = mm.load_feature_cache(str(tmp_path / "test_f.pt"))
+    assert keys is None and feats.shape == (7, 16)
+
+
+def test_construct_dataset_host_logic(mm, tmp_path, monkeypatch):
+    import mmrs_b200.search as S
+    names = ["a", "b"]
+    for c in names:
+        os.makedirs(tmp_path / c)
+        for i in range(3):
+            (tmp_path / c / f"{i}.jpg").write_bytes(b"x")
+    monkeypatch.setattr(S, "class_names", names)
+    monkeypatch.setattr(S, "class_to_idx", {"a": 0, "b": 1})
+    monkeypatch.setattr(S, "dataset_path", str(tmp_path))
+    fd = {f"{c}/{i}.jpg": np.full(4, ci * 10 + i, dtype=np.float32) for ci, c in enumerate(names) for i in range(3)}
+    feats, targets = S.construct_dataset(fd, ["1.jpg"], "b")
+    assert feats.shape == (5, 4) and targets.tolist().count(1) == 2 and targets.tolist().count(0) == 3
+    assert 11.0 not in feats[:, 0].tolist()

@@ -1,0 +1,209 @@
+"""Parity of the CUDA search path with the oracle (all calls go through the C ABI)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from golden_inputs import similarity_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+def explain_index_mismatches(got_i, want_i, want_v, tol):
+    """north_star: identical top-k indices, ties by index.  fp32 accumulation order differs between
+    MKL and any GPU kernel, so a differing position is accepted ONLY if the
+    reference's own scores of the two rows involved lie within `tol`.  Returns #mismatches."""
+    bad = (got_i != want_i)
+    n_bad = int(bad.sum())
+    if n_bad == 0:
+        return 0
+    for q, j in zip(*np.nonzero(bad)):
+        # the row we returned at position j must be one whose reference score is within tol of
+        # the reference's j-th score
+        lo, hi = max(0, j - 8), min(want_v.shape[1], j + 9)
+        near = np.abs(want_v[q, lo:hi] - want_v[q, j]) <= tol
+        cand = set(want_i[q, lo:hi][near].tolist())
+        assert int(got_i[q, j]) in cand or j == want_v.shape[1] - 1, (q, j, got_i[q, j], want_i[q, j])
+    return n_bad
+
+
+def check_fp32(mm, oracle, g, q, k, **kw):
+    want_v, want_i = oracle.search_topk(q, g, k, mode="fp32", **kw)
+    v, i = mm.search_topk(q, mm.DeviceGallery(g, mode="fp32"), k, **kw)
+    assert v.shape == (q.shape[0], k) and i.dtype == torch.int64 and v.dtype == torch.float32
+    scale = abs(kw.get("scale", 1.0))
+    np.testing.assert_allclose(v.cpu().numpy(), want_v.numpy(), atol=1e-5 * max(scale, 1.0), rtol=0)
+    n_bad = explain_index_mismatches(i.cpu().numpy(), want_i.numpy(), want_v.numpy(), 1e-5 * max(scale, 1.0))
+    assert n_bad <= max(1, i.numel() // 200), n_bad
+    # descending, ties by ascending index
+    vv, ii = v.cpu().numpy(), i.cpu().numpy()
+    assert np.all(vv[:, 1:] <= vv[:, :-1])
+    same = vv[:, 1:] == vv[:, :-1]
+    assert np.all(ii[:, 1:][same] > ii[:, :-1][same])
+    return n_bad
+
+
+@pytest.mark.parametrize("n,d,nq,k", [
+    (1, 8, 1, 1), (5, 8, 3, 5), (127, 64, 2, 10), (128, 64, 4, 128), (129, 64, 5, 100),
+    (1000, 100, 7, 10),            # D not a multiple of 8: zero-padded columns
+    (4096, 512, 9, 100), (16384, 32, 3, 10), (16385, 32, 3, 10), (20000, 768, 8, 100),
+    (70001, 64, 6, 1), (70001, 64, 17, 1024), (300000, 128, 2, 100),
+])
+def test_topk_fp32_matches_oracle(mm, oracle, n, d, nq, k):
+    g = oracle.synthetic_gallery(n, d, seed=n % 97, dtype=torch.float32)
+    q = oracle.synthetic_queries(nq, d, seed=d)
+    check_fp32(mm, oracle, g, q, k)
+
+
+def test_config_c1_shape_fp32(mm, oracle):
+    """C1: 10k x 512 gallery, 100 queries, top-10 cosine, fp32 mode (BASELINE.json configs[0]).
+    Nearly collinear features like a random-init ViT-B/32 gives: a common direction
+    plus small noise, so scores differ only in the 3rd decimal -- the stress test for H1."""
+    gen = torch.Generator().manual_seed(1)
+    base = torch.randn(512, generator=gen)
+    g = oracle.l2_normalize(base + 0.1 * torch.randn(10_000, 512, generator=gen))
+    q = base + 0.1 * torch.randn(100, 512, generator=gen)
+    n_bad = check_fp32(mm, oracle, g, q, 10)
+    print("C1-shape near-tie index mismatches:", n_bad)
+
+
+def test_scale_and_unnormalised_queries(mm, oracle):
+    g = oracle.synthetic_gallery(3000, 64, seed=1, dtype=torch.float32)
+    q = oracle.synthetic_queries(4, 64) * 3.0
+    check_fp32(mm, oracle, g, q, 20, normalize_queries=False, scale=100.0)
+    check_fp32(mm, oracle, g, q, 20, normalize_queries=True, scale=-1.0)   # negative scale: smallest cosine first
+
+
+def test_exact_ties_fall_to_lower_index(mm, oracle):
+    g = oracle.synthetic_gallery(40_000, 64, seed=2, dtype=torch.float32)
+    q = oracle.synthetic_queries(3, 64)
+    best = oracle.search_topk(q, g, 1)[1][:, 0]
+    for b in best.tolist():                 # replicate each query's best row at scattered places
+        for pos in (7, 12_345, 39_999, 20_000):
+            g[pos] = g[b]
+    want_v, want_i = oracle.search_topk(q, g, 10)
+    v, i = mm.search_topk(q, mm.DeviceGallery(g), 10)
+    assert torch.equal(i.cpu(), want_i)
+    # and the duplicates really are exact ties in OUR arithmetic
+    vv = v.cpu().numpy()
+    assert (vv[:, 0] == vv[:, 1]).all()
+
+
+def test_bf16_mode_recall_and_scores(mm, oracle):
+    g = oracle.synthetic_gallery(200_000, 512, seed=0, dtype=torch.bfloat16)
+    q = oracle.synthetic_queries(4, 512)
+    want_v, want_i = oracle.search_topk(q, g, 100, mode="bf16")
+    v, i = mm.search_topk(q, mm.DeviceGallery(g), 100)
+    assert mm.DeviceGallery(g).mode == "bf16"
+    np.testing.assert_allclose(v.cpu().numpy(), want_v.numpy(), atol=1e-2, rtol=0)   # north_star tolerance
+    hits = sum(len(set(a) & set(b)) for a, b in zip(i.cpu().tolist(), want_i.tolist()))
+    assert hits / want_i.numel() >= 0.999
+    # in practice far tighter: bf16 products are exact in fp32, only the summation order differs
+    assert np.abs(v.cpu().numpy() - want_v.numpy()).max() < 1e-5
+
+
+def test_overflow_falls_back_to_exhaustive(mm, oracle):
+    """Scores correlated with the tile-stride pattern: every tile OUTSIDE the seed sample beats the
+    sample, so the candidate list overflows and the exhaustive path must still be exact."""
+    n, d = 70_000, 32
+    g = oracle.synthetic_gallery(n, d, seed=5, dtype=torch.float32)
+    q = oracle.synthetic_queries(2, d)
+    qn = oracle.l2_normalize(q)
+    tiles = torch.arange(n) // 128
+    outside = (tiles % 16 != 0)
+    g[outside] = oracle.l2_normalize(g[outside] + 2.0 * qn[0])      # all of them score high for query 0
+    check_fp32(mm, oracle, g, q, 10)
+
+
+def test_host_and_device_queries_agree(mm, oracle):
+    g = oracle.synthetic_gallery(50_000, 256, seed=8, dtype=torch.bfloat16)
+    gal = mm.DeviceGallery(g)
+    q = oracle.synthetic_queries(3, 256)
+    vh, ih = mm.search_topk(q, gal, 50)                 # host in -> host out (C ABI *_host entry)
+    vd, idd = mm.search_topk(q.cuda(), gal, 50)         # device in -> device out
+    assert not vh.is_cuda and vd.is_cuda
+    assert torch.equal(ih, idd.cpu()) and torch.equal(vh, vd.cpu())
+    # numpy in
+    vn, inn = mm.search_topk(q.numpy(), gal, 50)
+    assert torch.equal(inn, ih)
+
+
+def test_row_offset_and_merge(mm, oracle):
+    g = oracle.synthetic_gallery(30_000, 64, seed=3, dtype=torch.float32)
+    g[10] = g[29_000]
+    q = oracle.synthetic_queries(5, 64)
+    want_v, want_i = oracle.search_topk(q, g, 25)
+    vs, is_ = [], []
+    for lo, hi in mm.shard_bounds(30_000, 4):
+        v, i = mm.search_topk(q.cuda(), mm.DeviceGallery(g[lo:hi], row_offset=lo), 25)
+        vs.append(v); is_.append(i)
+    from mmrs_b200.sharded import _merge_cuda
+    v, i = _merge_cuda(torch.stack(vs), torch.stack(is_), 25)
+    assert torch.equal(i.cpu(), want_i)
+    np.testing.assert_allclose(v.cpu().numpy(), want_v.numpy(), atol=1e-5)
+    ov, oi = oracle.merge_topk(torch.stack(vs).cpu(), torch.stack(is_).cpu(), 25)
+    assert torch.equal(i.cpu(), oi) and torch.equal(v.cpu(), ov)
+
+
+def test_edge_cases(mm, oracle):
+    g = oracle.synthetic_gallery(100, 16, seed=1, dtype=torch.float32)
+    gal = mm.DeviceGallery(g)
+    v, i = mm.search_topk(torch.empty(0, 16), gal, 5)
+    assert v.shape == (0, 5) and i.shape == (0, 5)
+    with pytest.raises(RuntimeError, match="out of range"):
+        mm.search_topk(torch.randn(1, 16), gal, 101)
+    q = torch.randn(3, 16); q[1] = 0
+    with pytest.raises(mm._cabi.MmrsError) as e:
+        mm.search_topk(q, gal, 5)                       # reference would give NaN (no eps at :157)
+    assert e.value.code == mm._cabi.ERR_ZERO_NORM
+    v, i = mm.search_topk(q, gal, 5, normalize_queries=False)   # a zero query is fine un-normalised
+    assert i[1].tolist() == [0, 1, 2, 3, 4] and (v[1] == 0).all()
+    with pytest.raises(ValueError):
+        mm.search_topk(torch.randn(1, 8), gal, 5)
+
+
+def test_full_scores_and_get_similarity_golden(mm, oracle):
+    gold = np.load(GOLDEN / "search_image_golden.npz")
+    for name, (features, targets, label, ref) in similarity_inputs().items():
+        pos, neg = mm.get_similarity(features, targets, label, ref)
+        assert pos.dtype == np.float32 and pos.shape == gold[f"{name}_pos"].shape
+        # scale 100: 1e-5 relative to the cosine == 1e-3 on these scores
+        np.testing.assert_allclose(pos, gold[f"{name}_pos"], atol=1e-3, rtol=0)
+        np.testing.assert_allclose(neg, gold[f"{name}_neg"], atol=1e-3, rtol=0)
+        s = mm.full_scores(ref[None], features, normalize_queries=False, scale=1.0)
+        want = oracle.full_scores(ref[None], features, normalize_queries=False)
+        np.testing.assert_allclose(s.numpy(), want.numpy(), atol=1e-5, rtol=0)
+    # multi-class scoring in one call (CLIP/lab3.py:113-114 loops over 5 classes)
+    g = oracle.synthetic_gallery(5000, 768, seed=4, dtype=torch.float32)
+    t = oracle.synthetic_queries(5, 768)
+    s = mm.full_scores(t, g)
+    np.testing.assert_allclose(s.numpy(), oracle.full_scores(t, g).numpy(), atol=1e-5, rtol=0)
+
+
+def test_threshold_sweep_golden(mm, oracle):
+    gold = np.load(GOLDEN / "search_image_golden.npz")
+    for name in ("small", "clip512", "taiyi768"):
+        pos, neg = gold[f"{name}_pos"], gold[f"{name}_neg"]
+        assert mm.find_thresholds(pos, neg, name) == gold[f"{name}_best_f1"]
+        for t, want in zip(gold[f"{name}_probe"], gold[f"{name}_eval"]):
+            got = np.array(mm.eval_threshold(pos, neg, t), dtype=np.float64)
+            np.testing.assert_array_equal(got, want)
+    rng = np.random.default_rng(0)
+    pos = rng.normal(1, 1, 100_000).astype(np.float32); neg = rng.normal(0, 1, 1_000_000).astype(np.float32)
+    thr = np.linspace(min(pos.min(), neg.min()), max(pos.max(), neg.max()), 200)
+    tp, fp = mm.threshold_sweep_counts(pos, neg, thr)
+    np.testing.assert_array_equal(tp, [(pos >= t).sum() for t in thr])
+    np.testing.assert_array_equal(fp, [(neg >= t).sum() for t in thr])
+
+
+@pytest.mark.parametrize("nq", [1, 4])
+def test_full_size_c2_small_batch(mm, oracle, nq):
+    """C2 at full size: 1M x 512 bf16, top-100 (the oracle takes seconds for <= 4 queries)."""
+    g = oracle.synthetic_gallery(1_000_000, 512, seed=0, dtype=torch.bfloat16)
+    q = oracle.synthetic_queries(nq, 512, seed=1)
+    want_v, want_i = oracle.search_topk(q, g, 100, mode="bf16")
+    v, i = mm.search_topk(q, mm.DeviceGallery(g), 100)
+    np.testing.assert_allclose(v.numpy(), want_v.numpy(), atol=1e-2, rtol=0)
+    hits = sum(len(set(a) & set(b)) for a, b in zip(i.tolist(), want_i.tolist()))
+    assert hits / want_i.numel() >= 0.999
+    assert explain_index_mismatches(i.numpy(), want_i.numpy(), want_v.numpy(), 1e-6) <= 2
