@@ -180,6 +180,21 @@ int mmrs_threshold_sweep(const float* d_pos, int64_t n_pos, const float* d_neg, 
                          int64_t* d_out_counts, void* d_workspace, size_t workspace_bytes,
                          void* stream);
 
+/* ---- measurement hooks (bench.py; not needed by a product caller) --------------------------- */
+
+/* Number of kernels this library has launched in this process (monotonic). */
+int64_t mmrs_launch_count(void);
+
+/*
+ * While enabled, every gallery-scan kernel launch (K1 / K2; the HBM- or tensor-bound kernels) is
+ * bracketed by CUDA events on the caller's stream.  mmrs_profile_read() synchronises those events,
+ * returns up to `cap` records (oldest first) and clears the log: duration in ms, kind
+ * (MMRS_PATH_GEMV or MMRS_PATH_MMA), and the algorithmic gallery bytes the launch streamed
+ * (rows visited * dim * element size).  Returns the number of records written.
+ */
+int mmrs_profile_enable(int on);
+int mmrs_profile_read(float* h_ms, int32_t* h_kind, int64_t* h_bytes, int64_t* h_flops, int32_t cap);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -7,6 +7,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 #include "plan.h"
 
@@ -43,6 +47,30 @@ static int fail(int code, const char* fmt, ...) {
       return fail(MMRS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__),  \
                   __FILE__, __LINE__);                                                      \
   } while (0)
+
+// ---- measurement hooks ---------------------------------------------------------------------------
+static std::atomic<long long> g_launches{0};
+struct ProfRec { cudaEvent_t e0, e1; int32_t kind; int64_t bytes; int64_t flops; };
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;
+static std::atomic<int> g_prof_on{0};
+
+#define MMRS_LAUNCH(expr)        \
+  do {                           \
+    g_launches.fetch_add(1);     \
+    MMRS_CUDA(expr);             \
+  } while (0)
+
+static int64_t rows_in_schedule(const TileSchedule& s, int64_t n_rows) {
+  int64_t rows = 0;
+  for (int64_t j = 0; j < s.n_sel; ++j) {
+    const int64_t t = j * s.tile_inc;
+    if (s.tile_exc != 0 && t % s.tile_exc == 0) continue;
+    const int64_t r0 = t * kTileRows;
+    rows += (n_rows - r0) < kTileRows ? (n_rows - r0) : kTileRows;
+  }
+  return rows;
+}
 
 struct DeviceInfo {
   int device = -1;
@@ -163,6 +191,28 @@ static Path choose_path(int32_t requested, int32_t dtype, int32_t n_queries) {
   return Path::kGemv;
 }
 
+template <typename F>
+static int profiled_scan(int32_t kind, int32_t dtype, const ScanParams& p, cudaStream_t stream, F launch) {
+  g_launches.fetch_add(1);
+  if (!g_prof_on.load(std::memory_order_relaxed)) {
+    MMRS_CUDA(launch());
+    return MMRS_OK;
+  }
+  ProfRec r{};
+  r.kind = kind;
+  const int64_t rows = rows_in_schedule(p.sched, p.n_rows);
+  r.bytes = rows * p.dim * (dtype == MMRS_DTYPE_BF16 ? 2 : 4);
+  r.flops = 2 * rows * p.dim * p.nq;
+  MMRS_CUDA(cudaEventCreate(&r.e0));
+  MMRS_CUDA(cudaEventCreate(&r.e1));
+  MMRS_CUDA(cudaEventRecord(r.e0, stream));
+  MMRS_CUDA(launch());
+  MMRS_CUDA(cudaEventRecord(r.e1, stream));
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof.push_back(r);
+  return MMRS_OK;
+}
+
 // One scan over the tiles of `sched` for queries [q_lo, q_hi) of the prepared matrices.
 static int run_scan(Path path, const DeviceInfo& dev, int32_t dtype, ScanParams base,
                     const Workspace& w, int32_t n_q_padded, int32_t q_lo, int32_t q_hi, int mode,
@@ -173,7 +223,10 @@ static int run_scan(Path path, const DeviceInfo& dev, int32_t dtype, ScanParams 
       ScanParams p = base;
       p.q0 = q;
       p.nq = (q_hi - q) < chunk ? (q_hi - q) : chunk;
-      MMRS_CUDA(launch_scan_mma(p, w.q_bf16, n_q_padded, mode, w.flags, dev.sm_count, stream));
+      int rc = profiled_scan(MMRS_PATH_MMA, dtype, p, stream, [&]() {
+        return launch_scan_mma(p, w.q_bf16, n_q_padded, mode, w.flags, dev.sm_count, stream);
+      });
+      if (rc != MMRS_OK) return rc;
     }
     return MMRS_OK;
   }
@@ -182,7 +235,10 @@ static int run_scan(Path path, const DeviceInfo& dev, int32_t dtype, ScanParams 
     ScanParams p = base;
     p.q0 = q;
     p.nq = (q_hi - q) < chunk ? (q_hi - q) : chunk;
-    MMRS_CUDA(launch_scan_gemv(p, dtype, mode, dev.sm_count, stream));
+    int rc = profiled_scan(MMRS_PATH_GEMV, dtype, p, stream, [&]() {
+      return launch_scan_gemv(p, dtype, mode, dev.sm_count, stream);
+    });
+    if (rc != MMRS_OK) return rc;
   }
   return MMRS_OK;
 }
@@ -213,7 +269,7 @@ static int enqueue_search(const SearchArgs& a, const DeviceInfo& dev, const Work
     return fail(MMRS_ERR_ARG, "MMRS_PATH_MMA needs a bf16 gallery");
 
   MMRS_CUDA(cudaMemsetAsync(w.flags, 0, 8 * sizeof(int32_t), stream));
-  MMRS_CUDA(launch_prep_queries(a.d_queries, a.n_queries, a.ldq_in, a.dim, a.normalize,
+  MMRS_LAUNCH(launch_prep_queries(a.d_queries, a.n_queries, a.ldq_in, a.dim, a.normalize,
                                 a.dtype == MMRS_DTYPE_BF16, w.q_f32, w.q_bf16, qp, ldq, w.flags,
                                 stream));
   ScanParams base{};
@@ -243,7 +299,7 @@ static int enqueue_search(const SearchArgs& a, const DeviceInfo& dev, const Work
       sp.out_indices = a.d_indices + static_cast<int64_t>(s0) * a.k;
       sp.index_offset = a.index_offset;
       sp.flags = w.flags;
-      MMRS_CUDA(launch_select(sp, ns, stream));
+      MMRS_LAUNCH(launch_select(sp, ns, stream));
     }
   }
   return MMRS_OK;
@@ -266,14 +322,14 @@ static int enqueue_exhaustive(const SearchArgs& a, const DeviceInfo& dev, const 
     ScanParams p = base;
     p.cand = w.cand - static_cast<int64_t>(q) * all_rows;
     p.q0 = q; p.nq = 1;
-    MMRS_CUDA(launch_scan_gemv(p, a.dtype, kModeDense, dev.sm_count, stream));
+    MMRS_LAUNCH(launch_scan_gemv(p, a.dtype, kModeDense, dev.sm_count, stream));
     SelectParams sp{};
     sp.cand = w.cand; sp.cnt = w.cnt; sp.thr = w.thr; sp.cap = all_rows;
     sp.fixed_n = all_rows; sp.k = a.k; sp.final_pass = 1;
     sp.out_values = a.d_values + static_cast<int64_t>(q) * a.k;
     sp.out_indices = a.d_indices + static_cast<int64_t>(q) * a.k;
     sp.index_offset = a.index_offset; sp.flags = w.flags;
-    MMRS_CUDA(launch_select(sp, 1, stream));
+    MMRS_LAUNCH(launch_select(sp, 1, stream));
   }
   return MMRS_OK;
 }
@@ -356,7 +412,7 @@ int mmrs_full_scores(const void* d_gallery, int64_t n_rows, int32_t dim, int64_t
   if (p == Path::kMma && gallery_dtype != MMRS_DTYPE_BF16)
     return fail(MMRS_ERR_ARG, "MMRS_PATH_MMA needs a bf16 gallery");
   MMRS_CUDA(cudaMemsetAsync(w.flags, 0, 8 * sizeof(int32_t), stream));
-  MMRS_CUDA(launch_prep_queries(d_queries, n_queries, ld_queries, dim, normalize_queries,
+  MMRS_LAUNCH(launch_prep_queries(d_queries, n_queries, ld_queries, dim, normalize_queries,
                                 gallery_dtype == MMRS_DTYPE_BF16, w.q_f32, w.q_bf16, qp, ldq,
                                 w.flags, stream));
   ScanParams base{};
@@ -501,12 +557,12 @@ int mmrs_topk_merge(const float* d_values_in, const int64_t* d_indices_in, int32
   uint64_t* cand = reinterpret_cast<uint64_t*>(static_cast<char*>(d_workspace) + align_up(8 * sizeof(int32_t), 256));
   const int32_t cap = n_lists * k_in;
   MMRS_CUDA(cudaMemsetAsync(flags, 0, 8 * sizeof(int32_t), stream));
-  MMRS_CUDA(launch_pack_keys(d_values_in, d_indices_in, n_lists, n_queries, k_in, cand, cap, stream));
+  MMRS_LAUNCH(launch_pack_keys(d_values_in, d_indices_in, n_lists, n_queries, k_in, cand, cap, stream));
   SelectParams sp{};
   sp.cand = cand; sp.cnt = nullptr; sp.thr = nullptr; sp.cap = cap; sp.fixed_n = cap;
   sp.k = k_out; sp.final_pass = 1; sp.out_values = d_out_values; sp.out_indices = d_out_indices;
   sp.index_offset = 0; sp.flags = flags;
-  MMRS_CUDA(launch_select(sp, n_queries, stream));
+  MMRS_LAUNCH(launch_select(sp, n_queries, stream));
   int32_t* h = pinned_status();
   if (!h) return fail(MMRS_ERR_CUDA, "cudaHostAlloc for the status word failed");
   MMRS_CUDA(cudaMemcpyAsync(h, flags, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
@@ -538,7 +594,7 @@ int mmrs_selfjoin_pairs(const void* d_emb, int64_t n_rows, int32_t dim, int64_t 
   if (capacity < 0 || (capacity > 0 && !d_out_pairs) || !d_out_count)
     return fail(MMRS_ERR_ARG, "bad output arguments");
   MMRS_CUDA(cudaMemsetAsync(d_out_count, 0, sizeof(int64_t), stream));
-  MMRS_CUDA(launch_selfjoin_f32(static_cast<const float*>(d_emb), n_rows, dim, ld_emb, threshold,
+  MMRS_LAUNCH(launch_selfjoin_f32(static_cast<const float*>(d_emb), n_rows, dim, ld_emb, threshold,
                                 row_begin, row_end, d_out_pairs, capacity, d_out_count,
                                 dev.sm_count, stream));
   int32_t* h = pinned_status();
@@ -549,6 +605,33 @@ int mmrs_selfjoin_pairs(const void* d_emb, int64_t n_rows, int32_t dim, int64_t 
   if (h64[0] > capacity)
     return fail(MMRS_ERR_CAPACITY, "%lld pairs found, capacity %lld", (long long)h64[0], (long long)capacity);
   return MMRS_OK;
+}
+
+int64_t mmrs_launch_count(void) { return g_launches.load(); }
+
+int mmrs_profile_enable(int on) {
+  g_prof_on.store(on ? 1 : 0);
+  return MMRS_OK;
+}
+
+int mmrs_profile_read(float* h_ms, int32_t* h_kind, int64_t* h_bytes, int64_t* h_flops, int32_t cap) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  int n = 0;
+  for (ProfRec& r : g_prof) {
+    float ms = -1.f;
+    if (cudaEventSynchronize(r.e1) == cudaSuccess) cudaEventElapsedTime(&ms, r.e0, r.e1);
+    if (n < cap) {
+      if (h_ms) h_ms[n] = ms;
+      if (h_kind) h_kind[n] = r.kind;
+      if (h_bytes) h_bytes[n] = r.bytes;
+      if (h_flops) h_flops[n] = r.flops;
+      ++n;
+    }
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  g_prof.clear();
+  return n;
 }
 
 size_t mmrs_threshold_sweep_workspace_bytes(int32_t n_thresholds) {
@@ -568,7 +651,7 @@ int mmrs_threshold_sweep(const float* d_pos, int64_t n_pos, const float* d_neg, 
     return fail(MMRS_ERR_ARG, "bad arguments");
   if (!d_workspace || workspace_bytes < mmrs_threshold_sweep_workspace_bytes(n_thresholds))
     return fail(MMRS_ERR_WORKSPACE, "workspace too small");
-  MMRS_CUDA(launch_threshold_sweep(d_pos, n_pos, d_neg, n_neg, d_thresholds, n_thresholds,
+  MMRS_LAUNCH(launch_threshold_sweep(d_pos, n_pos, d_neg, n_neg, d_thresholds, n_thresholds,
                                    d_out_counts, static_cast<unsigned long long*>(d_workspace),
                                    dev.sm_count, stream));
   return MMRS_OK;

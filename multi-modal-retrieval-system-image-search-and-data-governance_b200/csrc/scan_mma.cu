@@ -1,10 +1,387 @@
-// scan_mma.cu -- K2 placeholder (replaced by the tcgen05 kernel).
+// scan_mma.cu -- K2: tcgen05 tensor-core scan for batched queries over a bf16 gallery.
+//
+// "Batched queries really are a dense contraction" (BASELINE.json): scores[128 rows, Q] =
+// G_tile[128, D] * Qmat[Q, D]^T, both operands K-major bf16.  One persistent CTA per SM walks its
+// share of the 128-row gallery tiles:
+//
+//   warp 0 (one lane)  TMA producer: per 64-column k-block one 128x64 gallery box (HBM stream)
+//                      and one Qx64 query box (L2 resident) into a SWIZZLE_128B smem ring
+//   warp 1 (one lane)  tcgen05.mma issuer: D[tmem] (+)= A[smem] * B[smem], M=128, N=Q, K=16;
+//                      tcgen05.commit frees the smem slot / publishes the accumulator
+//   warp 2             TMEM allocator (2 accumulator stages of Q fp32 columns)
+//   warps 4..7         epilogue: tcgen05.ld the 128xQ accumulator (one gallery row per thread)
+//                      and run the same three epilogues as K1 -- the score matrix never reaches
+//                      HBM unless kModeScores asks for it.
+//
+// The accumulator is double buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Roofline: HBM-bound (N*D*2 bytes per pass) up to Q ~ 200, tensor-bound beyond
+// (SURVEY.md section 8d).
+#include <cuda.h>
+
 #include "common.cuh"
+
 namespace mmrs {
-int scan_mma_max_queries() { return 256; }
-bool scan_mma_available() { return false; }
-cudaError_t launch_scan_mma(const ScanParams&, const __nv_bfloat16*, int32_t, int, int32_t*, int,
-                            cudaStream_t) {
-  return cudaErrorNotSupported;
+
+constexpr int kMmaThreads = 256;
+constexpr int kBlockM = kTileRows;       // gallery rows per tile == UMMA M
+constexpr int kBlockK = 64;              // bf16 elements per k-block == one 128-byte swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kMaxQ = 256;               // UMMA N limit
+constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KiB
+constexpr int kMaxStages = 8;
+constexpr uint32_t kWatchdogSpins = 1u << 24;
+
+struct MmaShared {
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+  volatile uint32_t abort;
+  float thr[kMaxQ];
+};
+
+struct MmaCfg {
+  int32_t n_umma;        // UMMA N: queries of this pass rounded up to 16
+  int32_t k_blocks;      // ceil(dim / 64)
+  int32_t stages;
+  int32_t tmem_cols;     // power of two >= 2 * n_umma, >= 32
+  int32_t acc_stride;    // column offset between the two accumulator stages
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a pipeline bug must end the kernel with a status flag, not hang the GPU.
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, MmaShared* sh, int32_t* flags) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (sh->abort) return false;
+    if (++spins > kWatchdogSpins) {
+      sh->abort = 1;
+      atomicOr(flags, kFlagWatchdog);
+      return false;
+    }
+  }
+  return true;
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                            int32_t c0, int32_t c1, uint64_t cache_hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0),
+      "r"(c1), "l"(cache_hint)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns: thread i of the warp gets TMEM lane (base + i)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"): rows are 128 bytes,
+// 8-row core groups are 1024 bytes apart (SBO); LBO is unused for swizzled K-major layouts.
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3ffffu) >> 4);       // start address, bits [0,14)
+  d |= static_cast<uint64_t>(1) << 16;                           // leading byte offset (>>4), unused
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;                   // stride byte offset (>>4)
+  d |= static_cast<uint64_t>(1) << 46;                           // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(2) << 61;                           // layout type: SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M=128, N=n.
+__host__ __device__ constexpr uint32_t make_idesc(uint32_t n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((kBlockM >> 4) << 24);
+}
+
+constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;   // gallery: streamed once
+constexpr uint64_t kEvictLast = 0x14F0000000000000ull;    // queries: re-read by every tile
+
+template <int MODE>
+__global__ void __launch_bounds__(kMmaThreads, 1)
+scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_q,
+                const ScanParams p, const MmaCfg cfg, int32_t* flags) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // dynamic smem: [stages x (A 16 KiB | B n_umma*128 B)] then MmaShared; the ring must be
+  // 1024-byte aligned for the 128-byte swizzle
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t b_bytes = static_cast<uint32_t>(cfg.n_umma) * kBlockK * 2;
+  const uint32_t stage_bytes = kABytes + b_bytes;
+  MmaShared* sh = reinterpret_cast<MmaShared*>(ring + static_cast<size_t>(cfg.stages) * stage_bytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < cfg.stages; ++s) { mbar_init(&sh->full[s], 1); mbar_init(&sh->empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&sh->tmem_full[a], 1); mbar_init(&sh->tmem_empty[a], 4); }
+    sh->abort = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_g)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_q)) : "memory");
+  }
+  for (int c = threadIdx.x; c < kMaxQ; c += kMmaThreads) {
+    float t = __int_as_float(0x7f800000);  // +inf: padded columns never pass the filter
+    if (MODE == kModeFilter && c < p.nq) t = p.thr[p.q0 + c];
+    sh->thr[c] = t;
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)),
+                 "r"(static_cast<uint32_t>(cfg.tmem_cols))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = sh->tmem_base;
+
+  const int n_sel = p.sched.n_sel, inc = p.sched.tile_inc, exc = p.sched.tile_exc;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      bool ok = true;
+      for (int j = blockIdx.x; j < n_sel && ok; j += gridDim.x) {
+        const int t = j * inc;
+        if (exc != 0 && (t % exc) == 0) continue;
+        const int32_t row0 = t * kBlockM;
+        for (int kb = 0; kb < cfg.k_blocks; ++kb) {
+          if (!mbar_wait(&sh->empty[stage], phase ^ 1, sh, flags)) { ok = false; break; }
+          uint8_t* a_dst = ring + static_cast<size_t>(stage) * stage_bytes;
+          mbar_expect_tx(&sh->full[stage], stage_bytes);
+          tma_load_2d(a_dst, &map_g, &sh->full[stage], kb * kBlockK, row0, kEvictFirst);
+          tma_load_2d(a_dst + kABytes, &map_q, &sh->full[stage], kb * kBlockK, p.q0, kEvictLast);
+          if (++stage == static_cast<uint32_t>(cfg.stages)) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(static_cast<uint32_t>(cfg.n_umma));
+      uint32_t stage = 0, phase = 0, it = 0;
+      bool ok = true;
+      for (int j = blockIdx.x; j < n_sel && ok; j += gridDim.x) {
+        const int t = j * inc;
+        if (exc != 0 && (t % exc) == 0) continue;
+        const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+        if (!mbar_wait(&sh->tmem_empty[as], aphase ^ 1, sh, flags)) break;
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + as * static_cast<uint32_t>(cfg.acc_stride);
+        for (int kb = 0; kb < cfg.k_blocks; ++kb) {
+          if (!mbar_wait(&sh->full[stage], phase, sh, flags)) { ok = false; break; }
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(ring + static_cast<size_t>(stage) * stage_bytes);
+          const uint64_t adesc = make_sw128_desc(a_addr);
+          const uint64_t bdesc = make_sw128_desc(a_addr + kABytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            // advancing 16 bf16 along K inside the swizzled 128-byte row = +32 bytes = +2 in the
+            // (>>4) start-address field
+            umma_bf16(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
+                      (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&sh->empty[stage]);   // smem slot reusable once these MMAs retire
+          if (++stage == static_cast<uint32_t>(cfg.stages)) { stage = 0; phase ^= 1; }
+        }
+        if (ok) umma_commit(&sh->tmem_full[as]);   // accumulator complete
+        ++it;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: TMEM -> registers -> keys / scores =====
+    const int ew = warp - 4;                      // == warp % 4: the TMEM lane quarter this warp may read
+    const int r_in_tile = ew * 32 + lane;
+    const int64_t last_row = p.n_rows - 1;
+    uint32_t it = 0;
+    bool ok = true;
+    for (int j = blockIdx.x; j < n_sel && ok; j += gridDim.x) {
+      const int t = j * inc;
+      if (exc != 0 && (t % exc) == 0) continue;
+      const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+      if (!mbar_wait(&sh->tmem_full[as], aphase, sh, flags)) break;
+      tcgen05_fence_after();
+      const int64_t row = static_cast<int64_t>(t) * kBlockM + r_in_tile;
+      const bool row_ok = row <= last_row;
+      const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
+                              as * static_cast<uint32_t>(cfg.acc_stride);
+      for (int c0 = 0; c0 < cfg.n_umma; c0 += 16) {
+        uint32_t acc[16];
+        __syncwarp();
+        tmem_ld16(taddr0 + static_cast<uint32_t>(c0), acc);
+        tmem_ld_wait();
+        if constexpr (MODE == kModeFilter) {
+          if (row_ok) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+              const float s = __uint_as_float(acc[c]) * p.scale;
+              if (!(s < sh->thr[c0 + c])) {
+                const int q = p.q0 + c0 + c;
+                const uint32_t pos = atomicAdd(p.cnt + q, 1u);
+                if (pos < static_cast<uint32_t>(p.cap))
+                  p.cand[static_cast<int64_t>(q) * p.cap + pos] = make_key(s, static_cast<uint32_t>(row));
+              }
+            }
+          }
+        } else if constexpr (MODE == kModeDense) {
+          const int64_t slot = static_cast<int64_t>(j) * kBlockM + r_in_tile;
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            if (c0 + c < p.nq) {
+              const float s = __uint_as_float(acc[c]) * p.scale;
+              p.cand[static_cast<int64_t>(p.q0 + c0 + c) * p.cap + slot] =
+                  row_ok ? make_key(s, static_cast<uint32_t>(row)) : 0ull;
+            }
+          }
+        } else {
+          if (row_ok) {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+              if (c0 + c < p.nq)
+                p.out_scores[static_cast<int64_t>(p.q0 + c0 + c) * p.ld_out + row] =
+                    __uint_as_float(acc[c]) * p.scale;
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh->tmem_empty[as]);
+      ++it;
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(static_cast<uint32_t>(cfg.tmem_cols))
+                 : "memory");
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] tensor with row stride ld (elements); box = [box_rows, 64 cols]
+static bool make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                     uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int scan_mma_max_queries() { return kMaxQ; }
+bool scan_mma_available() { return true; }
+
+cudaError_t launch_scan_mma(const ScanParams& p, const __nv_bfloat16* q_bf16, int32_t n_q_padded,
+                            int mode, int32_t* flags, int sm_count, cudaStream_t stream) {
+  if (p.nq < 1 || p.nq > kMaxQ) return cudaErrorInvalidValue;
+  if (p.n_rows > 0x7fffffffll - kBlockM) return cudaErrorInvalidValue;   // TMA coordinates are int32
+  MmaCfg cfg;
+  cfg.n_umma = (p.nq + 15) / 16 * 16;
+  cfg.k_blocks = (p.dim + kBlockK - 1) / kBlockK;
+  int cols = 32;
+  while (cols < 2 * cfg.n_umma) cols <<= 1;
+  cfg.tmem_cols = cols;
+  cfg.acc_stride = cols / 2;
+  const size_t stage_bytes = static_cast<size_t>(kABytes) + static_cast<size_t>(cfg.n_umma) * kBlockK * 2;
+  const size_t budget = 227 * 1024 - sizeof(MmaShared) - 1024;   // alignment slack
+  int stages = static_cast<int>(budget / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) return cudaErrorInvalidValue;
+  cfg.stages = stages;
+  const size_t smem = 1024 + stage_bytes * stages + sizeof(MmaShared);
+
+  CUtensorMap map_g, map_q;
+  if (!make_map(&map_g, p.gallery, static_cast<uint64_t>(p.n_rows), static_cast<uint64_t>(p.dim),
+                static_cast<uint64_t>(p.ld), kBlockM))
+    return cudaErrorNotSupported;
+  if (!make_map(&map_q, q_bf16, static_cast<uint64_t>(n_q_padded), static_cast<uint64_t>(p.ldq),
+                static_cast<uint64_t>(p.ldq), static_cast<uint32_t>(cfg.n_umma)))
+    return cudaErrorNotSupported;
+
+  int grid = sm_count;
+  if (grid > p.sched.n_sel) grid = p.sched.n_sel;
+  if (grid < 1) grid = 1;
+  auto go = [&](auto kernel) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    kernel<<<grid, kMmaThreads, smem, stream>>>(map_g, map_q, p, cfg, flags);
+    return cudaGetLastError();
+  };
+  switch (mode) {
+    case kModeScores: return go(scan_mma_kernel<kModeScores>);
+    case kModeDense: return go(scan_mma_kernel<kModeDense>);
+    default: return go(scan_mma_kernel<kModeFilter>);
+  }
+}
+
 }  // namespace mmrs

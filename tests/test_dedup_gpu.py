@@ -47,7 +47,6 @@ def test_same_folder_wrapper(mm, oracle, tmp_path):
     assert total == len(paths)
     # oracle: same embedding, oracle pairs, oracle greedy walk in file-size order
     from mmrs_b200.dedup import pixel_embedding
-    order_paths = sorted(paths, key=lambda p: os.path.getsize(p), reverse=True)
     # (files were deleted; recompute the expectation from a fresh copy)
     import shutil
     fresh = tmp_path.parent / (tmp_path.name + "_fresh")
