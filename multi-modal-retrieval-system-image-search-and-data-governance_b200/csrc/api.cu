@@ -111,8 +111,8 @@ static int env_int(const char* name, int dflt) {
 constexpr int kSuperChunk = 1024;  // queries sharing one set of candidate lists
 
 static SearchPlan plan_for(int64_t n_rows, int32_t k) {
-  return make_search_plan(n_rows, k, kTileRows, env_int("MMRS_RATIO_LOG2", 4),
-                          env_int("MMRS_DENSE_TILES", 64));
+  return make_search_plan(n_rows, k, kTileRows, env_int("MMRS_RATIO_LOG2", 5),
+                          env_int("MMRS_DENSE_TILES", 16));
 }
 
 static int32_t padded_dim(int32_t dim) { return (dim + 7) / 8 * 8; }
@@ -334,6 +334,80 @@ static int enqueue_exhaustive(const SearchArgs& a, const DeviceInfo& dev, const 
   return MMRS_OK;
 }
 
+// ---- CUDA-graph cache -----------------------------------------------------------------------------
+// A search is 7-9 short dependent launches in front of one long one; submitted one by one the GPU
+// idles between them (the host needs ~60 us to issue what the GPU runs in ~40 us, measured:
+// profiles/r01_v1_bench.json whole step 0.31 ms vs 0.24 ms of kernels).  The whole sequence
+// is therefore captured once per distinct call signature and replayed with one cudaGraphLaunch.
+// Everything baked into the graph -- pointers, shapes, scalars -- is part of the key.
+struct GraphKey {
+  const void* gallery; int64_t n_rows; int32_t dim; int64_t ld; int32_t dtype;
+  const float* d_queries; int32_t n_queries; int64_t ldq_in; int32_t k; int32_t normalize;
+  float scale; int64_t index_offset; int32_t path; float* d_values; int64_t* d_indices;
+  void* workspace; int device; int ratio_log2; int dense_tiles;
+  bool operator==(const GraphKey& o) const {
+    return gallery == o.gallery && n_rows == o.n_rows && dim == o.dim && ld == o.ld && dtype == o.dtype &&
+           d_queries == o.d_queries && n_queries == o.n_queries && ldq_in == o.ldq_in && k == o.k &&
+           normalize == o.normalize && scale == o.scale && index_offset == o.index_offset &&
+           path == o.path && d_values == o.d_values && d_indices == o.d_indices &&
+           workspace == o.workspace && device == o.device && ratio_log2 == o.ratio_log2 &&
+           dense_tiles == o.dense_tiles;
+  }
+};
+struct GraphEntry { GraphKey key; cudaGraphExec_t exec; uint64_t stamp; long long kernels; };
+static std::mutex g_graph_mu;
+static std::vector<GraphEntry> g_graphs;
+static uint64_t g_graph_clock = 0;
+constexpr size_t kMaxGraphs = 32;
+
+static int launch_search_graph(const SearchArgs& a, const DeviceInfo& dev, const Workspace& w,
+                               void* workspace, cudaStream_t stream) {
+  if (g_prof_on.load(std::memory_order_relaxed) || env_int("MMRS_NO_GRAPH", 0))
+    return enqueue_search(a, dev, w, stream);   // event-bracketed launches are issued directly
+  GraphKey key{a.gallery, a.n_rows, a.dim, a.ld, a.dtype, a.d_queries, a.n_queries, a.ldq_in, a.k,
+               a.normalize, a.scale, a.index_offset, a.path, a.d_values, a.d_indices, workspace,
+               dev.device, env_int("MMRS_RATIO_LOG2", 5), env_int("MMRS_DENSE_TILES", 16)};
+  cudaGraphExec_t exec = nullptr;
+  long long kernels = 0;
+  {
+    std::lock_guard<std::mutex> lk(g_graph_mu);
+    for (GraphEntry& e : g_graphs)
+      if (e.key == key) { e.stamp = ++g_graph_clock; exec = e.exec; kernels = e.kernels; break; }
+  }
+  if (exec) {
+    g_launches.fetch_add(kernels);   // a replay launches the same kernels the capture recorded
+  } else {
+    cudaGraph_t graph = nullptr;
+    const long long before = g_launches.load();
+    // capture on a private stream: the caller's may be the legacy default stream, which cannot
+    // capture; the instantiated graph is then launched into the caller's stream
+    static thread_local cudaStream_t cap_stream[64] = {};
+    if (!cap_stream[dev.device])
+      MMRS_CUDA(cudaStreamCreateWithFlags(&cap_stream[dev.device], cudaStreamNonBlocking));
+    cudaStream_t cs = cap_stream[dev.device];
+    MMRS_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+    const int rc = enqueue_search(a, dev, w, cs);
+    kernels = g_launches.load() - before;
+    const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+    if (rc != MMRS_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) return fail(MMRS_ERR_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(ce));
+    const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) return fail(MMRS_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
+    std::lock_guard<std::mutex> lk(g_graph_mu);
+    if (g_graphs.size() >= kMaxGraphs) {   // evict the least recently used
+      size_t victim = 0;
+      for (size_t i = 1; i < g_graphs.size(); ++i)
+        if (g_graphs[i].stamp < g_graphs[victim].stamp) victim = i;
+      cudaGraphExecDestroy(g_graphs[victim].exec);
+      g_graphs.erase(g_graphs.begin() + victim);
+    }
+    g_graphs.push_back(GraphEntry{key, exec, ++g_graph_clock, kernels});
+  }
+  MMRS_CUDA(cudaGraphLaunch(exec, stream));
+  return MMRS_OK;
+}
+
 static int flags_to_status(int32_t f) {
   if (f & kFlagZeroNorm)
     return fail(MMRS_ERR_ZERO_NORM, "a query row has zero L2 norm and normalize_queries is set");
@@ -474,7 +548,7 @@ static int search_common(SearchArgs a, const float* h_queries, float* h_values, 
     a.d_queries = dq;
     a.ldq_in = a.dim;
   }
-  rc = enqueue_search(a, dev, w, stream);
+  rc = launch_search_graph(a, dev, w, d_workspace, stream);
   if (rc != MMRS_OK) return rc;
   int32_t* h = pinned_status();
   if (!h) return fail(MMRS_ERR_CUDA, "cudaHostAlloc for the status word failed");

@@ -38,7 +38,9 @@ struct MmaShared {
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
   volatile uint32_t abort;
-  float thr[kMaxQ];
+  alignas(16) float thr[kMaxQ];
+  alignas(16) uint32_t ep_mask[4][kMaxQ];   // per epilogue warp: lanes of each column that pass the bound
+  alignas(16) uint32_t ep_base[4][kMaxQ];   // per epilogue warp: first slot reserved for each column
 };
 
 struct MmaCfg {
@@ -250,25 +252,78 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
       const bool row_ok = row <= last_row;
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
                               as * static_cast<uint32_t>(cfg.acc_stride);
+      if constexpr (MODE == kModeFilter) {
+        // Two sweeps so that no thread ever waits on a global atomic inside a divergent branch
+        // (the first version did: one L2 round trip per passing score, serialised per warp --
+        // 53 us per tile at 256 queries, profiles/r01_launches_b256.csv).
+        //   sweep 1: compare, ballot -> per-column lane masks in shared memory
+        //   claim  : lane l reserves slots for columns l, l+32, ... with ONE atomicAdd each
+        //            (all in flight together), bases go to shared memory
+        //   sweep 2: re-read the accumulator chunk from TMEM (cheap) and store the keys
+        uint32_t* wmask = sh->ep_mask[ew];
+        uint32_t* wbase = sh->ep_base[ew];
+        uint32_t chunk_any = 0;
+        for (int c0 = 0; c0 < cfg.n_umma; c0 += 16) {
+          uint32_t acc[16];
+          __syncwarp();
+          tmem_ld16(taddr0 + static_cast<uint32_t>(c0), acc);
+          tmem_ld_wait();
+          uint32_t bal[16];
+          uint32_t any = 0;
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const float s = __uint_as_float(acc[c]) * p.scale;
+            bal[c] = __ballot_sync(0xffffffffu, row_ok && !(s < sh->thr[c0 + c]));
+            any |= bal[c];
+          }
+          if (any) {
+            chunk_any |= 1u << (c0 >> 4);
+            if (lane == 0) {
+              uint4* dst = reinterpret_cast<uint4*>(wmask + c0);
+              dst[0] = make_uint4(bal[0], bal[1], bal[2], bal[3]);
+              dst[1] = make_uint4(bal[4], bal[5], bal[6], bal[7]);
+              dst[2] = make_uint4(bal[8], bal[9], bal[10], bal[11]);
+              dst[3] = make_uint4(bal[12], bal[13], bal[14], bal[15]);
+            }
+          }
+        }
+        if (chunk_any) {   // warp-uniform
+          __syncwarp();
+          for (int col = lane; col < cfg.n_umma; col += 32) {
+            if ((chunk_any >> (col >> 4)) & 1u) {
+              const uint32_t m = wmask[col];
+              if (m) wbase[col] = atomicAdd(p.cnt + p.q0 + col, static_cast<uint32_t>(__popc(m)));
+            }
+          }
+          __syncwarp();
+          for (int c0 = 0; c0 < cfg.n_umma; c0 += 16) {
+            if (!((chunk_any >> (c0 >> 4)) & 1u)) continue;
+            uint32_t acc[16];
+            __syncwarp();
+            tmem_ld16(taddr0 + static_cast<uint32_t>(c0), acc);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+              const uint32_t m = wmask[c0 + c];
+              if ((m >> lane) & 1u) {
+                const uint32_t pos = wbase[c0 + c] + __popc(m & ((1u << lane) - 1u));
+                if (pos < static_cast<uint32_t>(p.cap)) {
+                  const float s = __uint_as_float(acc[c]) * p.scale;
+                  p.cand[static_cast<int64_t>(p.q0 + c0 + c) * p.cap + pos] =
+                      make_key(s, static_cast<uint32_t>(row));
+                }
+              }
+            }
+          }
+          __syncwarp();
+        }
+      } else {
       for (int c0 = 0; c0 < cfg.n_umma; c0 += 16) {
         uint32_t acc[16];
         __syncwarp();
         tmem_ld16(taddr0 + static_cast<uint32_t>(c0), acc);
         tmem_ld_wait();
-        if constexpr (MODE == kModeFilter) {
-          if (row_ok) {
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-              const float s = __uint_as_float(acc[c]) * p.scale;
-              if (!(s < sh->thr[c0 + c])) {
-                const int q = p.q0 + c0 + c;
-                const uint32_t pos = atomicAdd(p.cnt + q, 1u);
-                if (pos < static_cast<uint32_t>(p.cap))
-                  p.cand[static_cast<int64_t>(q) * p.cap + pos] = make_key(s, static_cast<uint32_t>(row));
-              }
-            }
-          }
-        } else if constexpr (MODE == kModeDense) {
+        if constexpr (MODE == kModeDense) {
           const int64_t slot = static_cast<int64_t>(j) * kBlockM + r_in_tile;
 #pragma unroll
           for (int c = 0; c < 16; ++c) {
@@ -288,6 +343,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
             }
           }
         }
+      }
       }
       tcgen05_fence_before();
       __syncwarp();

@@ -1,0 +1,31 @@
+"""torchrun --nproc-per-node N tools/multigpu_check.py : sharded search + sharded self-join vs the oracle
+(NCCL all-gather + CUDA merge).  Rank 0 prints 'multigpu ok'."""
+import os, sys
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import torch, torch.distributed as dist
+import mmrs_b200
+from oracle import oracle
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+n, d, k = 400_000, 512, 100
+g = oracle.synthetic_gallery(n, d, seed=0, dtype=torch.bfloat16)
+g[17] = g[n - 5]                                  # a tie across the first and last shard
+sg = mmrs_b200.ShardedGallery.from_full(g, device=dev)
+for nq in (3, 24):
+    q = oracle.synthetic_queries(nq, d, seed=nq)
+    v, i = sg.search_topk(q.to(dev), k)
+    wv, wi = oracle.search_topk(q, g, k, mode="bf16")
+    bad = (i.cpu() != wi).sum().item()
+    assert bad <= 2, (rank, nq, bad)
+    assert (v.cpu() - wv).abs().max().item() < 1e-5
+x, planted = oracle.synthetic_dedup(30_000, 128, dup_frac=0.02, seed=5)
+pairs = sg.find_duplicate_pairs(mmrs_b200.dedup._device_f32(x, dev), 0.95)
+assert [tuple(p) for p in pairs.cpu().tolist()] == planted
+dist.barrier()
+if rank == 0:
+    print(f"multigpu ok: world={world}")
+dist.destroy_process_group()
