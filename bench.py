@@ -271,6 +271,15 @@ def main():
 
     # dominant kernel = the launches that stream the most gallery bytes (last phase of each search)
     recs = [(ms[i], kind[i], nbytes[i], flops[i]) for i in range(nrec) if ms[i] > 0]
+    all_recs = recs
+    recs = [r for r in all_recs if r[1] in (1, 2)]          # gallery scans only
+    per_step = nrec // max(args.steps, 1)
+    timeline = None
+    if per_step and nrec == per_step * args.steps:            # same launch sequence every step
+        names = {1: "scan_gemv", 2: "scan_mma", 3: "select", 4: "prep"}
+        timeline = [{"kernel": names.get(kind[j], "?"),
+                     "ms": sum(ms[s * per_step + j] for s in range(args.steps)) / args.steps}
+                    for j in range(per_step)]
     hbm_peak, tc_peak, peak_src = measured_peaks()
     roofline = None
     if recs:
@@ -337,6 +346,8 @@ def main():
         }
         if sweep:
             line["sweep"] = sweep
+        if timeline:
+            line["kernel_timeline_ms"] = timeline
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -110,9 +110,14 @@ static int env_int(const char* name, int dflt) {
 
 constexpr int kSuperChunk = 1024;  // queries sharing one set of candidate lists
 
-static SearchPlan plan_for(int64_t n_rows, int32_t k) {
-  return make_search_plan(n_rows, k, kTileRows, env_int("MMRS_RATIO_LOG2", 5),
-                          env_int("MMRS_DENSE_TILES", 16));
+// Every phase appends about k * ratio keys per query whatever its size, so the appends of a whole
+// search scale with n_queries * k * ratio * (#phases - 1): small batches take few, coarse phases
+// (launch-bound), large batches finer ones (append-bound).  Measured on B200: tools/tune_plan.sh.
+static SearchPlan plan_for(int64_t n_rows, int32_t k, int32_t n_queries) {
+  const int ratio_dflt = n_queries <= 32 ? 5 : (n_queries <= 96 ? 4 : 3);
+  const int dense_dflt = n_queries <= 32 ? 16 : 64;
+  return make_search_plan(n_rows, k, kTileRows, env_int("MMRS_RATIO_LOG2", ratio_dflt),
+                          env_int("MMRS_DENSE_TILES", dense_dflt));
 }
 
 static int32_t padded_dim(int32_t dim) { return (dim + 7) / 8 * 8; }
@@ -140,7 +145,7 @@ static Workspace carve(void* base, int64_t n_rows, int32_t dim, int32_t n_querie
   w.q_f32 = reinterpret_cast<float*>(take(static_cast<size_t>(qp) * ldq * sizeof(float)));
   w.q_bf16 = reinterpret_cast<__nv_bfloat16*>(take(static_cast<size_t>(qp) * ldq * sizeof(__nv_bfloat16)));
   if (with_lists) {
-    const SearchPlan pl = plan_for(n_rows, k);
+    const SearchPlan pl = plan_for(n_rows, k, n_queries);
     const int32_t qs = n_queries < kSuperChunk ? n_queries : kSuperChunk;
     w.thr = reinterpret_cast<float*>(take(static_cast<size_t>(qs) * sizeof(float)));
     w.cnt = reinterpret_cast<uint32_t*>(take(static_cast<size_t>(qs) * sizeof(uint32_t)));
@@ -192,17 +197,14 @@ static Path choose_path(int32_t requested, int32_t dtype, int32_t n_queries) {
 }
 
 template <typename F>
-static int profiled_scan(int32_t kind, int32_t dtype, const ScanParams& p, cudaStream_t stream, F launch) {
+static int profiled_launch(int32_t kind, int64_t bytes, int64_t flops, cudaStream_t stream, F launch) {
   g_launches.fetch_add(1);
   if (!g_prof_on.load(std::memory_order_relaxed)) {
     MMRS_CUDA(launch());
     return MMRS_OK;
   }
   ProfRec r{};
-  r.kind = kind;
-  const int64_t rows = rows_in_schedule(p.sched, p.n_rows);
-  r.bytes = rows * p.dim * (dtype == MMRS_DTYPE_BF16 ? 2 : 4);
-  r.flops = 2 * rows * p.dim * p.nq;
+  r.kind = kind; r.bytes = bytes; r.flops = flops;
   MMRS_CUDA(cudaEventCreate(&r.e0));
   MMRS_CUDA(cudaEventCreate(&r.e1));
   MMRS_CUDA(cudaEventRecord(r.e0, stream));
@@ -211,6 +213,13 @@ static int profiled_scan(int32_t kind, int32_t dtype, const ScanParams& p, cudaS
   std::lock_guard<std::mutex> lk(g_prof_mu);
   g_prof.push_back(r);
   return MMRS_OK;
+}
+
+template <typename F>
+static int profiled_scan(int32_t kind, int32_t dtype, const ScanParams& p, cudaStream_t stream, F launch) {
+  const int64_t rows = g_prof_on.load(std::memory_order_relaxed) ? rows_in_schedule(p.sched, p.n_rows) : 0;
+  return profiled_launch(kind, rows * p.dim * (dtype == MMRS_DTYPE_BF16 ? 2 : 4), 2 * rows * p.dim * p.nq,
+                         stream, launch);
 }
 
 // One scan over the tiles of `sched` for queries [q_lo, q_hi) of the prepared matrices.
@@ -262,16 +271,20 @@ struct SearchArgs {
 // Enqueue the whole fused search on `stream`.  Results are valid iff the flag word stays 0.
 static int enqueue_search(const SearchArgs& a, const DeviceInfo& dev, const Workspace& w,
                           cudaStream_t stream) {
-  const SearchPlan pl = plan_for(a.n_rows, a.k);
+  const SearchPlan pl = plan_for(a.n_rows, a.k, a.n_queries);
   const int32_t ldq = padded_dim(a.dim), qp = padded_queries(a.n_queries);
   const Path path = choose_path(a.path, a.dtype, a.n_queries);
   if (path == Path::kMma && a.dtype != MMRS_DTYPE_BF16)
     return fail(MMRS_ERR_ARG, "MMRS_PATH_MMA needs a bf16 gallery");
 
   MMRS_CUDA(cudaMemsetAsync(w.flags, 0, 8 * sizeof(int32_t), stream));
-  MMRS_LAUNCH(launch_prep_queries(a.d_queries, a.n_queries, a.ldq_in, a.dim, a.normalize,
-                                a.dtype == MMRS_DTYPE_BF16, w.q_f32, w.q_bf16, qp, ldq, w.flags,
-                                stream));
+  {
+    int rc = profiled_launch(4, 0, 0, stream, [&]() {
+      return launch_prep_queries(a.d_queries, a.n_queries, a.ldq_in, a.dim, a.normalize,
+                                 a.dtype == MMRS_DTYPE_BF16, w.q_f32, w.q_bf16, qp, ldq, w.flags, stream);
+    });
+    if (rc != MMRS_OK) return rc;
+  }
   ScanParams base{};
   base.gallery = a.gallery; base.n_rows = a.n_rows; base.ld = a.ld; base.dim = a.dim;
   base.queries = w.q_f32; base.ldq = ldq; base.scale = a.scale;
@@ -299,7 +312,8 @@ static int enqueue_search(const SearchArgs& a, const DeviceInfo& dev, const Work
       sp.out_indices = a.d_indices + static_cast<int64_t>(s0) * a.k;
       sp.index_offset = a.index_offset;
       sp.flags = w.flags;
-      MMRS_LAUNCH(launch_select(sp, ns, stream));
+      rc = profiled_launch(3, 0, 0, stream, [&]() { return launch_select(sp, ns, stream); });
+      if (rc != MMRS_OK) return rc;
     }
   }
   return MMRS_OK;
@@ -309,7 +323,7 @@ static int enqueue_search(const SearchArgs& a, const DeviceInfo& dev, const Work
 // becomes a key, one select over all of them.
 static int enqueue_exhaustive(const SearchArgs& a, const DeviceInfo& dev, const Workspace& w,
                               cudaStream_t stream) {
-  const SearchPlan pl = plan_for(a.n_rows, a.k);
+  const SearchPlan pl = plan_for(a.n_rows, a.k, a.n_queries);
   const int32_t ldq = padded_dim(a.dim);
   const int32_t all_rows = pl.n_tiles * kTileRows;
   ScanParams base{};
@@ -366,7 +380,7 @@ static int launch_search_graph(const SearchArgs& a, const DeviceInfo& dev, const
     return enqueue_search(a, dev, w, stream);   // event-bracketed launches are issued directly
   GraphKey key{a.gallery, a.n_rows, a.dim, a.ld, a.dtype, a.d_queries, a.n_queries, a.ldq_in, a.k,
                a.normalize, a.scale, a.index_offset, a.path, a.d_values, a.d_indices, workspace,
-               dev.device, env_int("MMRS_RATIO_LOG2", 5), env_int("MMRS_DENSE_TILES", 16)};
+               dev.device, env_int("MMRS_RATIO_LOG2", -1), env_int("MMRS_DENSE_TILES", -1)};
   cudaGraphExec_t exec = nullptr;
   long long kernels = 0;
   {

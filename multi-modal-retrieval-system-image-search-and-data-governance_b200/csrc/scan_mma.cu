@@ -30,6 +30,7 @@ constexpr int kMaxQ = 256;               // UMMA N limit
 constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KiB
 constexpr int kMaxStages = 8;
 constexpr uint32_t kWatchdogSpins = 1u << 24;
+constexpr uint32_t kStash = 8;            // parked candidates per epilogue thread before a flush
 
 struct MmaShared {
   uint64_t full[kMaxStages];
@@ -39,8 +40,7 @@ struct MmaShared {
   uint32_t tmem_base;
   volatile uint32_t abort;
   alignas(16) float thr[kMaxQ];
-  alignas(16) uint32_t ep_mask[4][kMaxQ];   // per epilogue warp: lanes of each column that pass the bound
-  alignas(16) uint32_t ep_base[4][kMaxQ];   // per epilogue warp: first slot reserved for each column
+  alignas(16) uint2 stash[4][kStash * 32];  // per epilogue thread: parked (column, score) pairs
 };
 
 struct MmaCfg {
@@ -253,70 +253,64 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
                               as * static_cast<uint32_t>(cfg.acc_stride);
       if constexpr (MODE == kModeFilter) {
-        // Two sweeps so that no thread ever waits on a global atomic inside a divergent branch
-        // (the first version did: one L2 round trip per passing score, serialised per warp --
-        // 53 us per tile at 256 queries, profiles/r01_launches_b256.csv).
-        //   sweep 1: compare, ballot -> per-column lane masks in shared memory
-        //   claim  : lane l reserves slots for columns l, l+32, ... with ONE atomicAdd each
-        //            (all in flight together), bases go to shared memory
-        //   sweep 2: re-read the accumulator chunk from TMEM (cheap) and store the keys
-        uint32_t* wmask = sh->ep_mask[ew];
-        uint32_t* wbase = sh->ep_base[ew];
-        uint32_t chunk_any = 0;
+        // One sweep over the accumulator; a passing (column, score) is parked in this thread's
+        // private shared-memory stash and the slots are claimed at the end of the tile, four
+        // atomicAdds in flight per lane, so a thread waits for ONE L2 round trip per tile instead
+        // of one per passing score (the first version did the latter inside the divergent branch:
+        // 53 us per tile at 256 queries; a two-sweep ballot variant spent 45 % of its samples
+        // re-walking columns: profiles/r01_k2_b64_source.txt).
+        uint2* my_stash = sh->stash[ew] + lane;          // [slot][lane]: conflict-free
+        uint32_t n_st = 0;
+        auto flush = [&]() {
+          for (uint32_t i0 = 0; i0 < n_st; i0 += 4) {
+            uint2 e[4];
+            uint32_t pos[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (i0 + u < n_st) {
+                e[u] = my_stash[(i0 + u) * 32];
+                pos[u] = atomicAdd(p.cnt + p.q0 + e[u].x, 1u);
+              }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (i0 + u < n_st && pos[u] < static_cast<uint32_t>(p.cap))
+                p.cand[static_cast<int64_t>(p.q0 + e[u].x) * p.cap + pos[u]] =
+                    make_key(__uint_as_float(e[u].y), static_cast<uint32_t>(row));
+          }
+          n_st = 0;
+        };
         for (int c0 = 0; c0 < cfg.n_umma; c0 += 16) {
           uint32_t acc[16];
           __syncwarp();
           tmem_ld16(taddr0 + static_cast<uint32_t>(c0), acc);
           tmem_ld_wait();
-          uint32_t bal[16];
-          uint32_t any = 0;
+          // branch-free pass mask for the 16 columns (one warp per scheduler runs this loop, so
+          // every taken branch would expose its full latency), then a short loop over set bits
+          const float4* thr4 = reinterpret_cast<const float4*>(sh->thr + c0);
+          uint32_t bits = 0;
 #pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            const float s = __uint_as_float(acc[c]) * p.scale;
-            bal[c] = __ballot_sync(0xffffffffu, row_ok && !(s < sh->thr[c0 + c]));
-            any |= bal[c];
-          }
-          if (any) {
-            chunk_any |= 1u << (c0 >> 4);
-            if (lane == 0) {
-              uint4* dst = reinterpret_cast<uint4*>(wmask + c0);
-              dst[0] = make_uint4(bal[0], bal[1], bal[2], bal[3]);
-              dst[1] = make_uint4(bal[4], bal[5], bal[6], bal[7]);
-              dst[2] = make_uint4(bal[8], bal[9], bal[10], bal[11]);
-              dst[3] = make_uint4(bal[12], bal[13], bal[14], bal[15]);
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const float4 t = thr4[c4];
+            const float tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float sc = __uint_as_float(acc[c4 * 4 + u]) * p.scale;
+              bits |= (sc < tv[u]) ? 0u : (1u << (c4 * 4 + u));
             }
+          }
+          if (!row_ok) bits = 0;
+          while (bits) {
+            const int c = __ffs(bits) - 1;
+            bits &= bits - 1;
+            uint32_t a = acc[0];
+#pragma unroll
+            for (int u = 1; u < 16; ++u) a = (c == u) ? acc[u] : a;
+            if (n_st == kStash) flush();
+            my_stash[n_st * 32] = make_uint2(static_cast<uint32_t>(c0 + c), __float_as_uint(__uint_as_float(a) * p.scale));
+            ++n_st;
           }
         }
-        if (chunk_any) {   // warp-uniform
-          __syncwarp();
-          for (int col = lane; col < cfg.n_umma; col += 32) {
-            if ((chunk_any >> (col >> 4)) & 1u) {
-              const uint32_t m = wmask[col];
-              if (m) wbase[col] = atomicAdd(p.cnt + p.q0 + col, static_cast<uint32_t>(__popc(m)));
-            }
-          }
-          __syncwarp();
-          for (int c0 = 0; c0 < cfg.n_umma; c0 += 16) {
-            if (!((chunk_any >> (c0 >> 4)) & 1u)) continue;
-            uint32_t acc[16];
-            __syncwarp();
-            tmem_ld16(taddr0 + static_cast<uint32_t>(c0), acc);
-            tmem_ld_wait();
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-              const uint32_t m = wmask[c0 + c];
-              if ((m >> lane) & 1u) {
-                const uint32_t pos = wbase[c0 + c] + __popc(m & ((1u << lane) - 1u));
-                if (pos < static_cast<uint32_t>(p.cap)) {
-                  const float s = __uint_as_float(acc[c]) * p.scale;
-                  p.cand[static_cast<int64_t>(p.q0 + c0 + c) * p.cap + pos] =
-                      make_key(s, static_cast<uint32_t>(row));
-                }
-              }
-            }
-          }
-          __syncwarp();
-        }
+        if (n_st) flush();
       } else {
       for (int c0 = 0; c0 < cfg.n_umma; c0 += 16) {
         uint32_t acc[16];
