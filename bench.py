@@ -220,16 +220,35 @@ def main():
     q_host = torch.randn((nq, args.dim), generator=torch.Generator().manual_seed(1)).pin_memory()
     q_dev = q_host.to(device)
 
-    def search_dev():
+    DEPTH = 2      # batches in flight: the host prepares step i+1 while the GPU runs step i
+
+    def search_dev(sync=True):
         if sg is not None:
             return sg.search_topk(q_dev, args.k, path=args.path)
-        return mmrs_b200.search_topk(q_dev, gal, args.k, path=args.path)
+        return mmrs_b200.search_topk(q_dev, gal, args.k, path=args.path, sync=sync)
 
-    def search_host():
+    def search_host(sync=True):
         if sg is not None:
             v, i = sg.search_topk(q_host.to(device, non_blocking=True), args.k, path=args.path)
             return v.cpu(), i.cpu()
-        return mmrs_b200.search_topk(q_host, gal, args.k, path=args.path)
+        return mmrs_b200.search_topk(q_host, gal, args.k, path=args.path, sync=sync)
+
+    def run_steps(fn, n):
+        """n steps with up to DEPTH batches in flight (single GPU); every batch's status is checked."""
+        if sg is not None:
+            out = None
+            for _ in range(n):
+                out = fn()
+            return out
+        inflight = []
+        out = None
+        for _ in range(n):
+            inflight.append(fn(sync=False))
+            if len(inflight) >= DEPTH:
+                out = inflight.pop(0).wait()
+        for pnd in inflight:
+            out = pnd.wait()
+        return out
 
     def barrier():
         if world > 1:
@@ -237,23 +256,28 @@ def main():
         torch.cuda.synchronize()
 
     # ---- value: device-resident, CUDA events ---------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
-        search_dev()
+    run_steps(search_dev, max(args.warmup, 3))
     barrier()
     launches0 = lib.mmrs_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
         barrier()
         ev0.record()
-        for _ in range(args.steps):
-            out = search_dev()
+        out = run_steps(search_dev, args.steps)
         ev1.record()
         barrier()
     ms_total = ev0.elapsed_time(ev1)
     launches = lib.mmrs_launch_count() - launches0
+    # synchronous per-call latency of the same search (one batch in flight, host blocks on each)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        search_dev()
+    torch.cuda.synchronize()
+    sync_call_ms = (time.perf_counter() - t0) / args.steps * 1e3
     # dominant-kernel duration: the same steps again with the library's CUDA-event hooks on (the
-    # hooks bracket every scan launch on the launching stream; while they are on the library
-    # issues the launches one by one instead of replaying its CUDA graph, the kernels are the same)
+    # hooks bracket every launch on the launching stream; while they are on the library issues
+    # the launches one by one instead of replaying its CUDA graph -- the kernels are the same)
     lib.mmrs_profile_enable(1)
     for _ in range(args.steps):
         search_dev()
@@ -294,23 +318,31 @@ def main():
                     "algorithmic_bytes_per_launch": big, "avg_launch_ms": avg_ms, "launches_timed": len(dom),
                     "tflops": dom[0][3] / (avg_ms / 1e3) / 1e12,
                     "scan_kernels_ms_per_step": scan_ms_per_step, "share_of_step": scan_ms_per_step / (ms_total / args.steps),
-                    "whole_step_frac": (args.rows * args.dim * 2) / (ms_total / args.steps / 1e3) / 1e9 / hbm_peak}
+                    "whole_step_frac": (args.rows * args.dim * 2) / (ms_total / args.steps / 1e3) / 1e9 / hbm_peak,
+                    "how": "CUDA events around every launch of the kernel, on the launching stream, over the same "
+                           f"{args.steps} steps re-run with the library's profiling hooks enabled"}
 
     # ---- e2e: host API, host buffers ---------------------------------------------------------------
-    for _ in range(3):
-        search_host()
+    run_steps(search_host, 3)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        hv, hi = search_host()
+    hv, hi = run_steps(search_host, args.steps)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     tt = torch.tensor([dt], device=device)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        search_host()
+    torch.cuda.synchronize()
+    e2e_sync_ms = (time.perf_counter() - t0) / args.steps * 1e3
     e2e = {"value": nq * args.steps / float(tt.item()), "unit": "queries/s",
            "h2d_bytes_per_step": nq * args.dim * 4, "d2h_bytes_per_step": nq * args.k * 12,
-           "ms_per_step": float(tt.item()) / args.steps * 1e3}
+           "ms_per_step": float(tt.item()) / args.steps * 1e3,
+           "mode": f"host API search_topk(sync=False), {DEPTH} batches in flight, every batch waited on and status-checked"
+                   if sg is None else "host API, one batch in flight",
+           "blocking_call_ms": e2e_sync_ms}
 
     sweep = None
     if args.sweep and world == 1:
@@ -343,6 +375,8 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": workload_config(args, world), "clocks": clocks.summary(), "e2e": e2e,
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "pipelining": f"{DEPTH} batches in flight" if sg is None else "none",
+            "blocking_call_ms": sync_call_ms,
         }
         if sweep:
             line["sweep"] = sweep

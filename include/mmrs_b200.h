@@ -62,6 +62,9 @@ extern "C" {
 #define MMRS_ERR_CAPACITY (-6)   /* output capacity too small (self-join pair buffer);
                                     the required count is still reported             */
 #define MMRS_ERR_INTERNAL (-7)
+#define MMRS_ERR_RETRY (-8)      /* asynchronous search only: a candidate list overflowed and the
+                                    batch must be repeated through the synchronous entry point
+                                    (which then takes the exhaustive path)                     */
 
 /* element types of the gallery / embedding matrix */
 #define MMRS_DTYPE_F32 0
@@ -130,6 +133,29 @@ int mmrs_search_topk_host(const void* d_gallery, int64_t n_rows, int32_t dim, in
                           int64_t index_offset, int32_t path, float* h_out_values,
                           int64_t* h_out_indices, void* d_workspace, size_t workspace_bytes,
                           void* stream);
+
+/*
+ * Asynchronous forms: enqueue everything on `stream` and return at once, so a caller can keep
+ * several batches in flight (the host prepares batch i+1 while the GPU runs batch i).  h_status is
+ * one int32 of PINNED host memory owned by the caller and distinct per batch in flight; after the
+ * stream (or an event recorded behind the call) has completed, mmrs_search_status(h_status) returns
+ * the outcome of that batch -- MMRS_OK, an error, or MMRS_ERR_RETRY.  Results are valid only when
+ * it returns MMRS_OK.  One workspace may be shared by consecutive calls on the same stream.
+ */
+int mmrs_search_topk_async(const void* d_gallery, int64_t n_rows, int32_t dim, int64_t ld_gallery,
+                           int32_t gallery_dtype, const float* d_queries, int32_t n_queries,
+                           int64_t ld_queries, int32_t k, int32_t normalize_queries, float scale,
+                           int64_t index_offset, int32_t path, float* d_out_values,
+                           int64_t* d_out_indices, void* d_workspace, size_t workspace_bytes,
+                           int32_t* h_status, void* stream);
+int mmrs_search_topk_host_async(const void* d_gallery, int64_t n_rows, int32_t dim,
+                                int64_t ld_gallery, int32_t gallery_dtype, const float* h_queries,
+                                int32_t n_queries, int64_t ld_queries, int32_t k,
+                                int32_t normalize_queries, float scale, int64_t index_offset,
+                                int32_t path, float* h_out_values, int64_t* h_out_indices,
+                                void* d_workspace, size_t workspace_bytes, int32_t* h_status,
+                                void* stream);
+int mmrs_search_status(const int32_t* h_status);
 
 /* ---- multi-GPU merge -------------------------------------------------------------------- */
 

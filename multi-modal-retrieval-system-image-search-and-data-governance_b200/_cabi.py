@@ -9,7 +9,7 @@ _PKG_DIR = Path(__file__).resolve().parent
 LIB_PATH = _PKG_DIR / "lib" / "libmmrs_b200.so"
 
 OK = 0
-ERR_ARG, ERR_CUDA, ERR_ARCH, ERR_WORKSPACE, ERR_ZERO_NORM, ERR_CAPACITY, ERR_INTERNAL = -1, -2, -3, -4, -5, -6, -7
+ERR_ARG, ERR_CUDA, ERR_ARCH, ERR_WORKSPACE, ERR_ZERO_NORM, ERR_CAPACITY, ERR_INTERNAL, ERR_RETRY = -1, -2, -3, -4, -5, -6, -7, -8
 DTYPE_F32, DTYPE_BF16 = 0, 1
 PATH_AUTO, PATH_GEMV, PATH_MMA = 0, 1, 2
 PATHS = {"auto": PATH_AUTO, "gemv": PATH_GEMV, "mma": PATH_MMA}
@@ -51,6 +51,11 @@ SIGNATURES = {
     "mmrs_search_host_staging_bytes": (_sz, [_i32, _i32, _i32]),
     "mmrs_search_topk_host": (C.c_int, [_vp, _i64, _i32, _i64, _i32, _vp, _i32, _i64, _i32, _i32,
                                         _f32, _i64, _i32, _vp, _vp, _vp, _sz, _vp]),
+    "mmrs_search_topk_async": (C.c_int, [_vp, _i64, _i32, _i64, _i32, _vp, _i32, _i64, _i32, _i32, _f32,
+                                         _i64, _i32, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "mmrs_search_topk_host_async": (C.c_int, [_vp, _i64, _i32, _i64, _i32, _vp, _i32, _i64, _i32, _i32,
+                                              _f32, _i64, _i32, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "mmrs_search_status": (C.c_int, [_vp]),
     "mmrs_topk_merge_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "mmrs_topk_merge": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
     "mmrs_selfjoin_workspace_bytes": (_sz, [_i64, _i32, _i32]),

@@ -72,6 +72,11 @@ static int64_t rows_in_schedule(const TileSchedule& s, int64_t n_rows) {
   return rows;
 }
 
+static int env_int_early(const char* name, int dflt) {
+  const char* s = getenv(name);
+  return (s && *s) ? atoi(s) : dflt;
+}
+
 struct DeviceInfo {
   int device = -1;
   int sm_count = 0;
@@ -98,6 +103,11 @@ static int current_device(DeviceInfo* info) {
     return fail(MMRS_ERR_ARCH, "device %d is compute capability %d.x; this library is sm_100a only",
                 dev, info->cc_major);
   return MMRS_OK;
+}
+
+bool pdl_enabled() {
+  static const bool on = env_int_early("MMRS_NO_PDL", 0) == 0;
+  return on;
 }
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -532,8 +542,11 @@ size_t mmrs_search_host_staging_bytes(int32_t dim, int32_t n_queries, int32_t k)
          align_up(static_cast<size_t>(n_queries) * k * sizeof(int64_t), 256);
 }
 
-static int search_common(SearchArgs a, const float* h_queries, float* h_values, int64_t* h_indices,
-                         void* d_workspace, size_t workspace_bytes, cudaStream_t stream) {
+// Validate, stage host queries (host_io), enqueue the search (graph replay) and the read-back of
+// the status word -- and of the results when host_io -- on `stream`.  Nothing is synchronised.
+static int search_enqueue(SearchArgs& a, const float* h_queries, float* h_values, int64_t* h_indices,
+                          void* d_workspace, size_t workspace_bytes, int32_t* h_status,
+                          cudaStream_t stream, DeviceInfo* dev_out, Workspace* w_out) {
   DeviceInfo dev;
   int rc = current_device(&dev);
   if (rc != MMRS_OK) return rc;
@@ -541,6 +554,8 @@ static int search_common(SearchArgs a, const float* h_queries, float* h_values, 
   const size_t staging = host_io ? mmrs_search_host_staging_bytes(a.dim, a.n_queries, a.k) : 0;
   rc = validate_search(a, d_workspace, workspace_bytes, staging);
   if (rc != MMRS_OK) return rc;
+  if (!h_status) return fail(MMRS_ERR_ARG, "null status pointer");
+  h_status[0] = 0;
   if (a.n_queries == 0) return MMRS_OK;
   if (!host_io && (!a.d_queries || !a.d_values || !a.d_indices))
     return fail(MMRS_ERR_ARG, "null query / output pointer");
@@ -564,13 +579,27 @@ static int search_common(SearchArgs a, const float* h_queries, float* h_values, 
   }
   rc = launch_search_graph(a, dev, w, d_workspace, stream);
   if (rc != MMRS_OK) return rc;
-  int32_t* h = pinned_status();
-  if (!h) return fail(MMRS_ERR_CUDA, "cudaHostAlloc for the status word failed");
-  MMRS_CUDA(cudaMemcpyAsync(h, w.flags, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  MMRS_CUDA(cudaMemcpyAsync(h_status, w.flags, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
   if (host_io) {
     MMRS_CUDA(cudaMemcpyAsync(h_values, a.d_values, vbytes, cudaMemcpyDeviceToHost, stream));
     MMRS_CUDA(cudaMemcpyAsync(h_indices, a.d_indices, ibytes, cudaMemcpyDeviceToHost, stream));
   }
+  if (dev_out) *dev_out = dev;
+  if (w_out) *w_out = w;
+  return MMRS_OK;
+}
+
+static int search_common(SearchArgs a, const float* h_queries, float* h_values, int64_t* h_indices,
+                         void* d_workspace, size_t workspace_bytes, cudaStream_t stream) {
+  int32_t* h = pinned_status();
+  if (!h) return fail(MMRS_ERR_CUDA, "cudaHostAlloc for the status word failed");
+  DeviceInfo dev;
+  Workspace w{};
+  int rc = search_enqueue(a, h_queries, h_values, h_indices, d_workspace, workspace_bytes, h, stream, &dev, &w);
+  if (rc != MMRS_OK || a.n_queries == 0) return rc;
+  const bool host_io = h_queries != nullptr;
+  const size_t vbytes = static_cast<size_t>(a.n_queries) * a.k * sizeof(float);
+  const size_t ibytes = static_cast<size_t>(a.n_queries) * a.k * sizeof(int64_t);
   MMRS_CUDA(cudaStreamSynchronize(stream));
   int32_t f = h[0];
   if (f == kFlagOverflow) {
@@ -616,6 +645,41 @@ int mmrs_search_topk_host(const void* d_gallery, int64_t n_rows, int32_t dim, in
   }
   return search_common(a, h_queries, h_out_values, h_out_indices, d_workspace, workspace_bytes,
                        static_cast<cudaStream_t>(stream));
+}
+
+int mmrs_search_topk_async(const void* d_gallery, int64_t n_rows, int32_t dim, int64_t ld_gallery,
+                           int32_t gallery_dtype, const float* d_queries, int32_t n_queries,
+                           int64_t ld_queries, int32_t k, int32_t normalize_queries, float scale,
+                           int64_t index_offset, int32_t path, float* d_out_values,
+                           int64_t* d_out_indices, void* d_workspace, size_t workspace_bytes,
+                           int32_t* h_status, void* stream) {
+  SearchArgs a{d_gallery, n_rows, dim, ld_gallery, gallery_dtype, d_queries, n_queries, ld_queries,
+               k, normalize_queries, scale, index_offset, path, d_out_values, d_out_indices};
+  return search_enqueue(a, nullptr, nullptr, nullptr, d_workspace, workspace_bytes, h_status,
+                        static_cast<cudaStream_t>(stream), nullptr, nullptr);
+}
+
+int mmrs_search_topk_host_async(const void* d_gallery, int64_t n_rows, int32_t dim, int64_t ld_gallery,
+                                int32_t gallery_dtype, const float* h_queries, int32_t n_queries,
+                                int64_t ld_queries, int32_t k, int32_t normalize_queries, float scale,
+                                int64_t index_offset, int32_t path, float* h_out_values,
+                                int64_t* h_out_indices, void* d_workspace, size_t workspace_bytes,
+                                int32_t* h_status, void* stream) {
+  if (n_queries > 0 && !h_queries) return fail(MMRS_ERR_ARG, "null host query pointer");
+  SearchArgs a{d_gallery, n_rows, dim, ld_gallery, gallery_dtype, nullptr, n_queries, ld_queries,
+               k, normalize_queries, scale, index_offset, path, nullptr, nullptr};
+  static const float dummy = 0.f;
+  if (n_queries == 0) h_queries = &dummy;
+  return search_enqueue(a, h_queries, h_out_values, h_out_indices, d_workspace, workspace_bytes,
+                        h_status, static_cast<cudaStream_t>(stream), nullptr, nullptr);
+}
+
+int mmrs_search_status(const int32_t* h_status) {
+  if (!h_status) return fail(MMRS_ERR_ARG, "null status pointer");
+  const int32_t f = h_status[0];
+  if (f == kFlagOverflow)
+    return fail(MMRS_ERR_RETRY, "a candidate list overflowed: repeat this batch through the synchronous entry point");
+  return flags_to_status(f);
 }
 
 size_t mmrs_topk_merge_workspace_bytes(int32_t n_lists, int32_t n_queries, int32_t k_in) {

@@ -59,6 +59,29 @@ __device__ __forceinline__ uint4 ldg_stream_16B(const void* p) {
   return r;
 }
 
+// ---- programmatic dependent launch ------------------------------------------------------------------
+// A search is a chain of short kernels.  Each one lets its successor start launching right away
+// (launch_dependents) and blocks on its predecessor's results only after its own prologue
+// (griddepcontrol.wait returns once the preceding grid has completed and its writes are visible),
+// so launch latency, TMEM allocation and barrier set-up overlap the predecessor's tail.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();   // api.cu: MMRS_NO_PDL=1 turns the launch attribute off
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- epilogue modes of the scan kernels ---------------------------------------------------
 enum ScanMode : int {
   kModeScores = 0,  // write fp32 scores to out[q, row]                  (full_scores)

@@ -70,6 +70,8 @@ __global__ void __launch_bounds__(kGemvThreads, 2) scan_gemv_kernel(const ScanPa
   // consecutive 16-byte words (conflict-free LDS.128).
   extern __shared__ float4 q_smem[];
   const int n_chunks = p.dim / CH;
+  pdl_launch_dependents();
+  pdl_wait();   // queries (prep kernel) and thresholds (previous select) come from predecessors
   for (int i = threadIdx.x; i < QN * H * n_chunks; i += kGemvThreads) {
     const int c = i % n_chunks;
     const int h = (i / n_chunks) % H;
@@ -190,8 +192,7 @@ static cudaError_t launch_gemv_mode(const ScanParams& p, int mode, int sm_count,
     int grid = sm_count * occ;
     if (grid > p.sched.n_sel) grid = p.sched.n_sel;
     if (grid < 1) grid = 1;
-    kernel<<<grid, kGemvThreads, smem, stream>>>(p);
-    return cudaGetLastError();
+    return launch_pdl(kernel, dim3(grid), dim3(kGemvThreads), smem, stream, p);
   };
   switch (mode) {
     case kModeScores: return go(scan_gemv_kernel<T, QN, R, kModeScores>);
@@ -225,6 +226,8 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(
     int32_t n_rows_padded, int32_t ld_out, int32_t* flags) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  pdl_launch_dependents();
+  pdl_wait();   // the previous search on this stream may still be reading the prepared queries
   if (row >= n_rows_padded) return;
   float inv_den = 1.f;
   const bool real = row < n_queries;
@@ -255,10 +258,8 @@ cudaError_t launch_prep_queries(const float* q, int32_t n_queries, int64_t ldq, 
                                 int32_t* flags, cudaStream_t stream) {
   const int warps_per_block = 8;
   const int grid = (n_rows_padded + warps_per_block - 1) / warps_per_block;
-  prep_queries_kernel<<<grid, warps_per_block * 32, 0, stream>>>(
-      q, n_queries, ldq, dim, normalize, round_bf16, out_f32, out_bf16, n_rows_padded, ld_out,
-      flags);
-  return cudaGetLastError();
+  return launch_pdl(prep_queries_kernel, dim3(grid), dim3(warps_per_block * 32), 0, stream, q, n_queries,
+                    ldq, dim, normalize, round_bf16, out_f32, out_bf16, n_rows_padded, ld_out, flags);
 }
 
 // ---- small fills ----------------------------------------------------------------------------

@@ -165,16 +165,18 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_g)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_q)) : "memory");
   }
-  for (int c = threadIdx.x; c < kMaxQ; c += kMmaThreads) {
-    float t = __int_as_float(0x7f800000);  // +inf: padded columns never pass the filter
-    if (MODE == kModeFilter && c < p.nq) t = p.thr[p.q0 + c];
-    sh->thr[c] = t;
-  }
+  pdl_launch_dependents();
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)),
                  "r"(static_cast<uint32_t>(cfg.tmem_cols))
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  pdl_wait();   // everything above overlaps the predecessor; its results are read from here on
+  for (int c = threadIdx.x; c < kMaxQ; c += kMmaThreads) {
+    float t = __int_as_float(0x7f800000);  // +inf: padded columns never pass the filter
+    if (MODE == kModeFilter && c < p.nq) t = p.thr[p.q0 + c];
+    sh->thr[c] = t;
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -424,8 +426,7 @@ cudaError_t launch_scan_mma(const ScanParams& p, const __nv_bfloat16* q_bf16, in
   auto go = [&](auto kernel) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    kernel<<<grid, kMmaThreads, smem, stream>>>(map_g, map_q, p, cfg, flags);
-    return cudaGetLastError();
+    return launch_pdl(kernel, dim3(grid), dim3(kMmaThreads), smem, stream, map_g, map_q, p, cfg, flags);
   };
   switch (mode) {
     case kModeScores: return go(scan_mma_kernel<kModeScores>);

@@ -25,6 +25,7 @@ constexpr int kSelWarps = kSelThreads / 32;
 constexpr int kSelMaxK = 1024;
 constexpr int kSelMaxKpt = 16;                     // register-resident lists: up to 16 Ki keys
 constexpr int kSelWinners = kSelMaxK + kSelMaxK / 4 + 8;
+constexpr int kSelBucket = 512;                    // bucket small enough for one warp to finish
 
 struct SelShared {
   uint32_t warp_cnt[2][kSelWarps];   // packed per-warp pivot counts, double buffered
@@ -32,6 +33,9 @@ struct SelShared {
   uint64_t red_min[kSelWarps];
   uint64_t red_max[kSelWarps];
   uint32_t n_out;
+  uint32_t n_bucket;
+  uint64_t thr_key;
+  uint64_t bucket[kSelBucket];
   uint64_t winners[kSelWinners];
 };
 
@@ -39,46 +43,45 @@ struct SelShared {
 // above it ends the descent; the (unsorted) keys above it become the next list.
 __device__ __forceinline__ uint32_t relaxed_limit(uint32_t k) { return k + k / 4 + 8; }
 
-__global__ void __launch_bounds__(kSelThreads, 1) select_topk_kernel(const SelectParams p) {
-  __shared__ SelShared sh;
-  const int q = blockIdx.x;
+// The walk towards the k-th largest key.  State: `prefix` with `pos` undecided low bits;
+// ge = #keys >= prefix (>= k), above = #keys >= prefix + 2^pos (< k).  One step tries the three
+// pivots prefix | d << (pos-2), d = 1..3, and keeps the largest with >= k keys at or above it.
+struct Walk {
+  uint64_t prefix;
+  int pos;
+  uint32_t ge, above;
+};
+__device__ __forceinline__ void walk_step(Walk& w, uint32_t k, uint32_t t1, uint32_t t2, uint32_t t3, int bits) {
+  const int shift = w.pos - bits;
+  // counts at the four digit boundaries, descending digit: t[3], t[2], t[1], ge
+  if (bits == 2 && t3 >= k) { w.prefix |= 3ull << shift; w.ge = t3; /* above unchanged */ }
+  else if (bits == 2 && t2 >= k) { w.prefix |= 2ull << shift; w.ge = t2; w.above = t3; }
+  else if (t1 >= k) { w.prefix |= 1ull << shift; w.ge = t1; w.above = bits == 2 ? t2 : w.above; }
+  else { w.above = t1; }
+  w.pos = shift;
+}
+
+template <int KPT>
+__device__ __forceinline__ void select_body(const SelectParams& p, SelShared& sh, uint64_t* list, uint32_t n,
+                                            int q) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  uint64_t* list = p.cand + static_cast<int64_t>(q) * p.cap;
-
-  uint32_t n;
-  if (p.fixed_n >= 0) {
-    n = static_cast<uint32_t>(p.fixed_n);
-  } else {
-    n = p.cnt[q];
-    if (n > static_cast<uint32_t>(p.cap)) {
-      if (tid == 0) atomicOr(p.flags, kFlagOverflow);
-      n = p.cap;
-    }
-  }
   const uint32_t k = p.k;
-  if (n < k) {  // cannot happen on a correct schedule; never read past the list
-    if (tid == 0) atomicOr(p.flags, kFlagShort);
-    return;
-  }
   const uint32_t limit = p.final_pass ? k : relaxed_limit(k);
+  constexpr bool in_regs = KPT > 0;
+  constexpr int R = in_regs ? KPT : 1;
 
-  // Lists up to 16 Ki keys live in registers, `kpt` (block-uniform) slots per thread; longer ones
-  // (the exhaustive fallback) are re-read from global memory at every step.
-  const int kpt = static_cast<int>((n + kSelThreads - 1) / kSelThreads);
-  const bool in_regs = kpt <= kSelMaxKpt;
-  uint64_t key[kSelMaxKpt];
-  if (in_regs) {
+  uint64_t key[R];
+  if constexpr (in_regs) {
 #pragma unroll
-    for (int i = 0; i < kSelMaxKpt; ++i) {
+    for (int i = 0; i < KPT; ++i) {
       const uint32_t idx = tid + i * kSelThreads;
-      key[i] = (i < kpt && idx < n) ? list[idx] : 0ull;   // 0 is below every real key
+      key[i] = idx < n ? list[idx] : 0ull;   // 0 is below every real key
     }
   }
   auto for_each_key = [&](auto&& f) {
-    if (in_regs) {
+    if constexpr (in_regs) {
 #pragma unroll
-      for (int i = 0; i < kSelMaxKpt; ++i)
-        if (i < kpt) f(key[i]);
+      for (int i = 0; i < KPT; ++i) f(key[i]);
     } else {
       // block-uniform trip count (the callbacks use warp collectives); 0 pads the tail
       for (uint32_t base = 0; base < n; base += kSelThreads) {
@@ -101,7 +104,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) select_topk_kernel(const Selec
     mx = b > mx ? b : mx;
   }
   if (lane == 0) { sh.red_min[warp] = mn; sh.red_max[warp] = mx; }
-  if (tid == 0) sh.n_out = 0;
+  if (tid == 0) { sh.n_out = 0; sh.n_bucket = 0; }
   __syncthreads();
   mn = sh.red_min[lane];
   mx = sh.red_max[lane];
@@ -113,21 +116,24 @@ __global__ void __launch_bounds__(kSelThreads, 1) select_topk_kernel(const Selec
     mx = b > mx ? b : mx;
   }
 
-  // ---- bit-wise descent towards the k-th largest key, 2 bits per step ---------------------------------
   uint64_t thr_key;
   if (n <= limit) {
     thr_key = mn;                        // every real key is selected
   } else {
     const uint64_t diff = mn ^ mx;
-    int pos = diff == 0 ? 0 : 64 - __clzll(static_cast<long long>(diff));   // undecided low bits
-    uint64_t prefix = pos >= 64 ? 0ull : (mx >> pos) << pos;
+    Walk w;
+    w.pos = diff == 0 ? 0 : 64 - __clzll(static_cast<long long>(diff));   // undecided low bits
+    w.prefix = w.pos >= 64 ? 0ull : (mx >> w.pos) << w.pos;
+    w.ge = n;       // zeros included: harmless, they are never >= a pivot
+    w.above = 0;
     int buf = 0;
-    while (pos > 0) {
-      const int w = pos >= 2 ? 2 : 1;
-      const int shift = pos - w;
-      const uint64_t p1 = prefix | (1ull << shift);
-      const uint64_t p2 = prefix | (2ull << shift);     // only meaningful when w == 2
-      const uint64_t p3 = prefix | (3ull << shift);
+    // ---- phase A: block-wide steps until the bucket [prefix, prefix + 2^pos) is small ------------
+    while (w.pos > 0 && w.ge > limit && (w.ge - w.above) > kSelBucket) {
+      const int bits = w.pos >= 2 ? 2 : 1;
+      const int shift = w.pos - bits;
+      const uint64_t p1 = w.prefix | (1ull << shift);
+      const uint64_t p2 = w.prefix | (2ull << shift);     // only meaningful when bits == 2
+      const uint64_t p3 = w.prefix | (3ull << shift);
       uint32_t c1 = 0, c2 = 0, c3 = 0;
       for_each_key([&](uint64_t x) {
         c1 += x >= p1;
@@ -135,7 +141,7 @@ __global__ void __launch_bounds__(kSelThreads, 1) select_topk_kernel(const Selec
         c3 += x >= p3;
       });
       uint32_t t1, t2, t3;
-      if (in_regs) {
+      if constexpr (in_regs) {
         // per-warp sums are <= 32 * 16 = 512: three 10-bit fields in one REDUX
         const uint32_t packed = __reduce_add_sync(0xffffffffu, c1 | (c2 << 10) | (c3 << 20));
         if (lane == 0) sh.warp_cnt[buf][warp] = packed;
@@ -156,16 +162,53 @@ __global__ void __launch_bounds__(kSelThreads, 1) select_topk_kernel(const Selec
         t2 = __reduce_add_sync(0xffffffffu, sh.wide_cnt[1][lane]);
         t3 = __reduce_add_sync(0xffffffffu, sh.wide_cnt[2][lane]);
       }
-      // counts are non-increasing in the pivot; take the largest pivot with >= k keys above it
-      uint32_t cnt_sel;
-      if (w == 2 && t3 >= k) { prefix = p3; cnt_sel = t3; }
-      else if (w == 2 && t2 >= k) { prefix = p2; cnt_sel = t2; }
-      else if (t1 >= k) { prefix = p1; cnt_sel = t1; }
-      else { cnt_sel = 0xffffffffu; }            // digit 0: prefix unchanged, count unknown (> limit)
-      pos = shift;
-      if (cnt_sel <= limit) break;               // final: exactly k keys are >= prefix
+      walk_step(w, k, t1, t2, t3, bits);
     }
-    thr_key = prefix;
+    // ---- phase B: one warp finishes on the bucket's keys ------------------------------------------
+    if (w.pos > 0 && w.ge > limit) {
+      const uint64_t lo = w.prefix;
+      const uint64_t hi_excl_minus1 = w.prefix | ((w.pos >= 64 ? ~0ull : ((1ull << w.pos) - 1ull)));
+      for_each_key([&](uint64_t x) {
+        const bool in = x >= lo && x <= hi_excl_minus1 && x != 0ull;
+        const uint32_t m = __ballot_sync(0xffffffffu, in);
+        if (m) {
+          uint32_t base = 0;
+          if (lane == 0) base = atomicAdd(&sh.n_bucket, static_cast<uint32_t>(__popc(m)));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (in) sh.bucket[base + __popc(m & ((1u << lane) - 1u))] = x;   // count <= kSelBucket by construction
+        }
+      });
+      __syncthreads();
+      if (warp == 0) {
+        const uint32_t nb = sh.n_bucket;
+        for (uint32_t idx = nb + lane; idx < kSelBucket; idx += 32) sh.bucket[idx] = 0ull;   // pad
+        __syncwarp();
+        const uint32_t n_it = (nb + 31) / 32;    // warp-uniform
+        const uint32_t base_above = w.above;     // keys above the bucket count for every pivot
+        while (w.pos > 0 && w.ge > limit) {
+          const int bits = w.pos >= 2 ? 2 : 1;
+          const int shift = w.pos - bits;
+          const uint64_t p1 = w.prefix | (1ull << shift);
+          const uint64_t p2 = w.prefix | (2ull << shift);
+          const uint64_t p3 = w.prefix | (3ull << shift);
+          uint32_t c1 = 0, c2 = 0, c3 = 0;
+          for (uint32_t i = 0; i < n_it; ++i) {       // keys stay in shared memory: no register cost
+            const uint64_t x = sh.bucket[lane + i * 32];
+            c1 += x >= p1;
+            c2 += x >= p2;
+            c3 += x >= p3;
+          }
+          const uint32_t packed = __reduce_add_sync(0xffffffffu, c1 | (c2 << 10) | (c3 << 20));
+          walk_step(w, k, base_above + (packed & 1023u), base_above + ((packed >> 10) & 1023u),
+                    base_above + (packed >> 20), bits);
+        }
+        if (lane == 0) sh.thr_key = w.prefix;
+      }
+      __syncthreads();
+      thr_key = sh.thr_key;
+    } else {
+      thr_key = w.prefix;
+    }
   }
 
   // ---- gather the winners -------------------------------------------------------------------------
@@ -209,11 +252,44 @@ __global__ void __launch_bounds__(kSelThreads, 1) select_topk_kernel(const Selec
   }
 }
 
+__global__ void __launch_bounds__(kSelThreads, 1) select_topk_kernel(const SelectParams p) {
+  __shared__ SelShared sh;
+  const int q = blockIdx.x;
+  const int tid = threadIdx.x;
+  uint64_t* list = p.cand + static_cast<int64_t>(q) * p.cap;
+  pdl_launch_dependents();
+  pdl_wait();   // the list and its length come from the preceding scan
+
+  uint32_t n;
+  if (p.fixed_n >= 0) {
+    n = static_cast<uint32_t>(p.fixed_n);
+  } else {
+    n = p.cnt[q];
+    if (n > static_cast<uint32_t>(p.cap)) {
+      if (tid == 0) atomicOr(p.flags, kFlagOverflow);
+      n = p.cap;
+    }
+  }
+  if (n < static_cast<uint32_t>(p.k)) {  // cannot happen on a correct schedule; never read past the list
+    if (tid == 0) atomicOr(p.flags, kFlagShort);
+    return;
+  }
+  // Lists up to 16 Ki keys live in registers, KPT slots per thread (instantiated per size so that
+  // a 2 000-key list does not pay for 16 predicated slots); longer ones (the exhaustive fallback)
+  // are re-read from global memory at every step.
+  const uint32_t kpt = (n + kSelThreads - 1) / kSelThreads;
+  if (kpt <= 1) select_body<1>(p, sh, list, n, q);
+  else if (kpt <= 2) select_body<2>(p, sh, list, n, q);
+  else if (kpt <= 4) select_body<4>(p, sh, list, n, q);
+  else if (kpt <= 8) select_body<8>(p, sh, list, n, q);
+  else if (kpt <= kSelMaxKpt) select_body<16>(p, sh, list, n, q);
+  else select_body<0>(p, sh, list, n, q);
+}
+
 cudaError_t launch_select(const SelectParams& p, int32_t n_queries, cudaStream_t stream) {
   if (n_queries <= 0) return cudaSuccess;
   if (p.k < 1 || p.k > kSelMaxK) return cudaErrorInvalidValue;
-  select_topk_kernel<<<n_queries, kSelThreads, 0, stream>>>(p);
-  return cudaGetLastError();
+  return launch_pdl(select_topk_kernel, dim3(n_queries), dim3(kSelThreads), 0, stream, p);
 }
 
 // (value, global index) -> key lists laid out [n_queries, cap] with cap = n_lists * k_in.

@@ -83,6 +83,21 @@ class DeviceGallery:
             self._workspaces[key] = buf
         return buf
 
+    def search_workspace(self, nq: int, k: int, host_io: bool):
+        """(aligned device pointer, byte size) of the scratch space of one search shape; sized by
+        the library's own query and cached, so a steady-state call allocates nothing."""
+        key = ("search", nq, k, host_io)
+        hit = self._workspaces.get(key)
+        if hit is None:
+            lib = _cabi.lib
+            nbytes = lib.mmrs_search_workspace_bytes(self.n_rows, self.padded_dim, self.dtype_code, max(nq, 1), k)
+            if host_io:
+                nbytes += lib.mmrs_search_host_staging_bytes(self.padded_dim, max(nq, 1), k)
+            buf = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=self.device)
+            hit = (buf, self.aligned_ptr(buf), int(nbytes))
+            self._workspaces[key] = hit
+        return hit[1], hit[2]
+
     @staticmethod
     def aligned_ptr(buf: torch.Tensor) -> int:
         p = buf.data_ptr()

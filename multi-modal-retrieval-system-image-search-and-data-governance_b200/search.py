@@ -59,8 +59,33 @@ def _prep_queries(queries, gal: DeviceGallery):
     return q, not q.is_cuda
 
 
+class PendingSearch:
+    """Handle of an asynchronous search (`search_topk(..., sync=False)`): `values` / `indices` are
+    filled once the work enqueued on the stream has run; `wait()` blocks until then, checks the
+    batch's status word and returns `(values, indices)` (repeating the batch synchronously in the
+    rare case a candidate list overflowed)."""
+
+    def __init__(self, values, indices, status, event, redo):
+        self.values, self.indices = values, indices
+        self._status, self._event, self._redo = status, event, redo
+        self._done = False
+
+    def wait(self):
+        if not self._done:
+            self._event.synchronize()
+            st = _cabi.lib.mmrs_search_status(self._status.data_ptr())
+            if st == _cabi.ERR_RETRY:
+                v, i = self._redo()
+                self.values.copy_(v)
+                self.indices.copy_(i)
+            else:
+                _cabi.check(st)
+            self._done = True
+        return self.values, self.indices
+
+
 def search_topk(queries, gallery: GalleryLike, k: int, *, normalize_queries: bool = True,
-                scale: float = 1.0, mode: Optional[str] = None, path: str = "auto"):
+                scale: float = 1.0, mode: Optional[str] = None, path: str = "auto", sync: bool = True):
     """Per-query top-k of `scale * q @ G.T` without materialising the score matrix.
 
     Returns `(values [Q, k] fp32 descending, indices [Q, k] int64)` exactly like
@@ -68,6 +93,8 @@ def search_topk(queries, gallery: GalleryLike, k: int, *, normalize_queries: boo
     by ascending row index; indices are global (`gallery.row_offset` added).
     Host queries (CPU tensor / numpy) give host results -- the reference's call shape
     (host in, `.cpu()` out, code/search_image.py:105-109) -- device queries give device results.
+    `sync=False` enqueues the search on the current stream and returns a PendingSearch, so several
+    batches can be in flight.
     """
     gal = _as_gallery(gallery, mode)
     q, on_host = _prep_queries(queries, gal)
@@ -78,29 +105,38 @@ def search_topk(queries, gallery: GalleryLike, k: int, *, normalize_queries: boo
     if k > gal.n_rows:
         raise RuntimeError("selected index k out of range")  # torch.topk's message
     lib = _cabi.lib
-    with torch.cuda.device(gal.device):
-        ws_bytes = lib.mmrs_search_workspace_bytes(gal.n_rows, gal.padded_dim, gal.dtype_code, max(nq, 1), k)
-        if on_host:
-            ws_bytes += lib.mmrs_search_host_staging_bytes(gal.padded_dim, max(nq, 1), k)
-            ws = gal.workspace(("search", nq, k, True), ws_bytes)
-            if nq > 0 and not q.is_pinned():
-                q = q.pin_memory()
-            values = torch.empty((nq, k), dtype=torch.float32, pin_memory=True)
-            indices = torch.empty((nq, k), dtype=torch.int64, pin_memory=True)
-            fn = lib.mmrs_search_topk_host
-        else:
-            ws = gal.workspace(("search", nq, k, False), ws_bytes)
-            values = torch.empty((nq, k), dtype=torch.float32, device=gal.device)
-            indices = torch.empty((nq, k), dtype=torch.int64, device=gal.device)
-            fn = lib.mmrs_search_topk
-        if nq == 0:
-            return values, indices
-        _cabi.check(fn(gal.data.data_ptr(), gal.n_rows, gal.padded_dim, gal.data.stride(0),
-                       gal.dtype_code, q.data_ptr(), nq, q.stride(0), k, int(bool(normalize_queries)),
-                       float(scale), gal.row_offset, _cabi.PATHS[path], values.data_ptr(),
-                       indices.data_ptr(), DeviceGallery.aligned_ptr(ws), ws_bytes,
-                       _stream_handle(gal.device)))
-    return values, indices
+    dev = gal.device
+    if torch.cuda.current_device() != dev.index:
+        torch.cuda.set_device(dev)
+    ws_ptr, ws_bytes = gal.search_workspace(nq, k, on_host)
+    if on_host:
+        if nq > 0 and not q.is_pinned():
+            q = q.pin_memory()
+        values = torch.empty((nq, k), dtype=torch.float32, pin_memory=True)
+        indices = torch.empty((nq, k), dtype=torch.int64, pin_memory=True)
+    else:
+        values = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        indices = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    if nq == 0:
+        return (values, indices) if sync else PendingSearch(values, indices, None, None, None)
+    args = (gal.data.data_ptr(), gal.n_rows, gal.padded_dim, gal.data.stride(0), gal.dtype_code,
+            q.data_ptr(), nq, q.stride(0), k, int(bool(normalize_queries)), float(scale),
+            gal.row_offset, _cabi.PATHS[path], values.data_ptr(), indices.data_ptr(), ws_ptr, ws_bytes)
+    stream = torch.cuda.current_stream(dev)
+    if sync:
+        fn = lib.mmrs_search_topk_host if on_host else lib.mmrs_search_topk
+        _cabi.check(fn(*args, stream.cuda_stream))
+        return values, indices
+    status = torch.zeros(1, dtype=torch.int32).pin_memory()
+    fn = lib.mmrs_search_topk_host_async if on_host else lib.mmrs_search_topk_async
+    _cabi.check(fn(*args, status.data_ptr(), stream.cuda_stream))
+    event = torch.cuda.Event()
+    event.record(stream)
+    pend = PendingSearch(values, indices, status, event,
+                         lambda: search_topk(queries, gal, k, normalize_queries=normalize_queries, scale=scale,
+                                             path=path, sync=True))
+    pend._keepalive = q        # the enqueued copies / kernels read it
+    return pend
 
 
 def full_scores(queries, gallery: GalleryLike, *, normalize_queries: bool = True, scale: float = 1.0,
