@@ -224,22 +224,16 @@ def main():
 
     def search_dev(sync=True):
         if sg is not None:
-            return sg.search_topk(q_dev, args.k, path=args.path)
+            return sg.search_topk(q_dev, args.k, path=args.path, sync=sync)
         return mmrs_b200.search_topk(q_dev, gal, args.k, path=args.path, sync=sync)
 
     def search_host(sync=True):
-        if sg is not None:
-            v, i = sg.search_topk(q_host.to(device, non_blocking=True), args.k, path=args.path)
-            return v.cpu(), i.cpu()
+        if sg is not None:     # host queries in, host results out (H2D and D2H inside the call)
+            return sg.search_topk(q_host, args.k, path=args.path, sync=sync)
         return mmrs_b200.search_topk(q_host, gal, args.k, path=args.path, sync=sync)
 
     def run_steps(fn, n):
-        """n steps with up to DEPTH batches in flight (single GPU); every batch's status is checked."""
-        if sg is not None:
-            out = None
-            for _ in range(n):
-                out = fn()
-            return out
+        """n steps with up to DEPTH batches in flight; every batch is waited on and status-checked."""
         inflight = []
         out = None
         for _ in range(n):
@@ -341,7 +335,7 @@ def main():
            "h2d_bytes_per_step": nq * args.dim * 4, "d2h_bytes_per_step": nq * args.k * 12,
            "ms_per_step": float(tt.item()) / args.steps * 1e3,
            "mode": f"host API search_topk(sync=False), {DEPTH} batches in flight, every batch waited on and status-checked"
-                   if sg is None else "host API, one batch in flight",
+                   if sg is None else f"ShardedGallery.search_topk(host queries, sync=False), {DEPTH} batches in flight",
            "blocking_call_ms": e2e_sync_ms}
 
     sweep = None
@@ -375,7 +369,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": workload_config(args, world), "clocks": clocks.summary(), "e2e": e2e,
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-            "pipelining": f"{DEPTH} batches in flight" if sg is None else "none",
+            "pipelining": f"{DEPTH} batches in flight",
             "blocking_call_ms": sync_call_ms,
         }
         if sweep:

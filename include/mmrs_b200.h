@@ -157,6 +157,28 @@ int mmrs_search_topk_host_async(const void* d_gallery, int64_t n_rows, int32_t d
                                 void* stream);
 int mmrs_search_status(const int32_t* h_status);
 
+/*
+ * Sharded search without a host round trip: each rank writes its local top-k as packed 64-bit keys
+ * (order-preserving fp32 score in the high word, ~global_row in the low word; a larger key is a
+ * better match and keys are unique), ONE all-gather moves n_queries * k * 8 bytes per rank, and
+ * mmrs_topk_merge_keys_async selects the global top-k_out straight from the gathered buffer
+ * [n_lists, list_stride] (each list = n_queries * k_in keys, list_stride >= that, in elements).
+ * d_out_keys must hold n_queries * k + 1 elements: the LAST one receives the shard's device status
+ * word (0 = ok, 1 = candidate-list overflow, ...), so it is gathered along with the keys and every
+ * rank can see whether any rank has to repeat the batch.  d_status is one device int32 of scratch,
+ * h_status as above.
+ */
+int mmrs_search_topk_keys_async(const void* d_gallery, int64_t n_rows, int32_t dim,
+                                int64_t ld_gallery, int32_t gallery_dtype, const float* d_queries,
+                                int32_t n_queries, int64_t ld_queries, int32_t k,
+                                int32_t normalize_queries, float scale, int64_t index_offset,
+                                int32_t path, uint64_t* d_out_keys, void* d_workspace,
+                                size_t workspace_bytes, int32_t* h_status, void* stream);
+int mmrs_topk_merge_keys_async(const uint64_t* d_keys_in, int32_t n_lists, int32_t n_queries,
+                               int32_t k_in, int64_t list_stride, int32_t k_out,
+                               float* d_out_values, int64_t* d_out_indices, int32_t* d_status,
+                               int32_t* h_status, void* stream);
+
 /* ---- multi-GPU merge -------------------------------------------------------------------- */
 
 size_t mmrs_topk_merge_workspace_bytes(int32_t n_lists, int32_t n_queries, int32_t k_in);

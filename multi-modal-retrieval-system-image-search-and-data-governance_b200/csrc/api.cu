@@ -124,8 +124,8 @@ constexpr int kSuperChunk = 1024;  // queries sharing one set of candidate lists
 // search scale with n_queries * k * ratio * (#phases - 1): small batches take few, coarse phases
 // (launch-bound), large batches finer ones (append-bound).  Measured on B200: tools/tune_plan.sh.
 static SearchPlan plan_for(int64_t n_rows, int32_t k, int32_t n_queries) {
-  const int ratio_dflt = n_queries <= 32 ? 5 : (n_queries <= 96 ? 4 : 3);
-  const int dense_dflt = n_queries <= 32 ? 16 : 64;
+  const int ratio_dflt = n_queries <= 128 ? 4 : 3;
+  const int dense_dflt = n_queries <= 32 ? 16 : (n_queries <= 64 ? 32 : 64);
   return make_search_plan(n_rows, k, kTileRows, env_int("MMRS_RATIO_LOG2", ratio_dflt),
                           env_int("MMRS_DENSE_TILES", dense_dflt));
 }
@@ -202,7 +202,8 @@ enum class Path { kGemv, kMma };
 static Path choose_path(int32_t requested, int32_t dtype, int32_t n_queries) {
   if (requested == MMRS_PATH_GEMV) return Path::kGemv;
   if (requested == MMRS_PATH_MMA) return Path::kMma;
-  if (dtype == MMRS_DTYPE_BF16 && n_queries > 4 && scan_mma_available()) return Path::kMma;
+  // measured on B200 (profiles/r01_tune3.log): K1 wins for 1-2 queries, K2 from 3 on
+  if (dtype == MMRS_DTYPE_BF16 && n_queries > 2 && scan_mma_available()) return Path::kMma;
   return Path::kGemv;
 }
 
@@ -276,6 +277,7 @@ struct SearchArgs {
   const float* d_queries; int32_t n_queries; int64_t ldq_in;
   int32_t k; int32_t normalize; float scale; int64_t index_offset; int32_t path;
   float* d_values; int64_t* d_indices;
+  uint64_t* d_keys = nullptr;   // optional: packed (score, ~global row) keys instead of / besides the pair
 };
 
 // Enqueue the whole fused search on `stream`.  Results are valid iff the flag word stays 0.
@@ -318,8 +320,9 @@ static int enqueue_search(const SearchArgs& a, const DeviceInfo& dev, const Work
       sp.fixed_n = ph == 0 ? pl.dense_rows : -1;
       sp.k = a.k;
       sp.final_pass = ph == pl.n_phases - 1;
-      sp.out_values = a.d_values + static_cast<int64_t>(s0) * a.k;
-      sp.out_indices = a.d_indices + static_cast<int64_t>(s0) * a.k;
+      sp.out_values = a.d_values ? a.d_values + static_cast<int64_t>(s0) * a.k : nullptr;
+      sp.out_indices = a.d_indices ? a.d_indices + static_cast<int64_t>(s0) * a.k : nullptr;
+      sp.out_keys = a.d_keys ? a.d_keys + static_cast<int64_t>(s0) * a.k : nullptr;
       sp.index_offset = a.index_offset;
       sp.flags = w.flags;
       rc = profiled_launch(3, 0, 0, stream, [&]() { return launch_select(sp, ns, stream); });
@@ -368,9 +371,9 @@ struct GraphKey {
   const void* gallery; int64_t n_rows; int32_t dim; int64_t ld; int32_t dtype;
   const float* d_queries; int32_t n_queries; int64_t ldq_in; int32_t k; int32_t normalize;
   float scale; int64_t index_offset; int32_t path; float* d_values; int64_t* d_indices;
-  void* workspace; int device; int ratio_log2; int dense_tiles;
+  void* workspace; int device; int ratio_log2; int dense_tiles; uint64_t* d_keys;
   bool operator==(const GraphKey& o) const {
-    return gallery == o.gallery && n_rows == o.n_rows && dim == o.dim && ld == o.ld && dtype == o.dtype &&
+    return d_keys == o.d_keys && gallery == o.gallery && n_rows == o.n_rows && dim == o.dim && ld == o.ld && dtype == o.dtype &&
            d_queries == o.d_queries && n_queries == o.n_queries && ldq_in == o.ldq_in && k == o.k &&
            normalize == o.normalize && scale == o.scale && index_offset == o.index_offset &&
            path == o.path && d_values == o.d_values && d_indices == o.d_indices &&
@@ -390,7 +393,7 @@ static int launch_search_graph(const SearchArgs& a, const DeviceInfo& dev, const
     return enqueue_search(a, dev, w, stream);   // event-bracketed launches are issued directly
   GraphKey key{a.gallery, a.n_rows, a.dim, a.ld, a.dtype, a.d_queries, a.n_queries, a.ldq_in, a.k,
                a.normalize, a.scale, a.index_offset, a.path, a.d_values, a.d_indices, workspace,
-               dev.device, env_int("MMRS_RATIO_LOG2", -1), env_int("MMRS_DENSE_TILES", -1)};
+               dev.device, env_int("MMRS_RATIO_LOG2", -1), env_int("MMRS_DENSE_TILES", -1), a.d_keys};
   cudaGraphExec_t exec = nullptr;
   long long kernels = 0;
   {
@@ -557,7 +560,7 @@ static int search_enqueue(SearchArgs& a, const float* h_queries, float* h_values
   if (!h_status) return fail(MMRS_ERR_ARG, "null status pointer");
   h_status[0] = 0;
   if (a.n_queries == 0) return MMRS_OK;
-  if (!host_io && (!a.d_queries || !a.d_values || !a.d_indices))
+  if (!host_io && (!a.d_queries || (!a.d_keys && (!a.d_values || !a.d_indices))))
     return fail(MMRS_ERR_ARG, "null query / output pointer");
   const Workspace w = carve(d_workspace, a.n_rows, a.dim, a.n_queries, a.k, true);
   const size_t vbytes = static_cast<size_t>(a.n_queries) * a.k * sizeof(float);
@@ -672,6 +675,57 @@ int mmrs_search_topk_host_async(const void* d_gallery, int64_t n_rows, int32_t d
   if (n_queries == 0) h_queries = &dummy;
   return search_enqueue(a, h_queries, h_out_values, h_out_indices, d_workspace, workspace_bytes,
                         h_status, static_cast<cudaStream_t>(stream), nullptr, nullptr);
+}
+
+int mmrs_search_topk_keys_async(const void* d_gallery, int64_t n_rows, int32_t dim, int64_t ld_gallery,
+                                int32_t gallery_dtype, const float* d_queries, int32_t n_queries,
+                                int64_t ld_queries, int32_t k, int32_t normalize_queries, float scale,
+                                int64_t index_offset, int32_t path, uint64_t* d_out_keys,
+                                void* d_workspace, size_t workspace_bytes, int32_t* h_status,
+                                void* stream) {
+  if (index_offset < 0 || index_offset + n_rows > 0x100000000ll)
+    return fail(MMRS_ERR_ARG, "global row ids must fit 32 bits");
+  SearchArgs a{d_gallery, n_rows, dim, ld_gallery, gallery_dtype, d_queries, n_queries, ld_queries,
+               k, normalize_queries, scale, index_offset, path, nullptr, nullptr};
+  a.d_keys = d_out_keys;
+  if (!d_out_keys) return fail(MMRS_ERR_ARG, "null key output pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint64_t* tail = d_out_keys + static_cast<int64_t>(n_queries < 0 ? 0 : n_queries) * k;
+  MMRS_CUDA(cudaMemsetAsync(tail, 0, sizeof(uint64_t), st));
+  Workspace w{};
+  int rc = search_enqueue(a, nullptr, nullptr, nullptr, d_workspace, workspace_bytes, h_status, st, nullptr, &w);
+  if (rc != MMRS_OK || n_queries == 0) return rc;
+  // the shard's status word travels with its keys, so that after the all-gather every rank knows
+  // whether ANY rank has to repeat the batch -- no second collective
+  MMRS_CUDA(cudaMemcpyAsync(tail, w.flags, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  return MMRS_OK;
+}
+
+int mmrs_topk_merge_keys_async(const uint64_t* d_keys_in, int32_t n_lists, int32_t n_queries, int32_t k_in,
+                               int64_t list_stride, int32_t k_out, float* d_out_values,
+                               int64_t* d_out_indices, int32_t* d_status, int32_t* h_status,
+                               void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceInfo dev;
+  int rc = current_device(&dev);
+  if (rc != MMRS_OK) return rc;
+  if (!h_status || !d_status) return fail(MMRS_ERR_ARG, "null status pointer");
+  h_status[0] = 0;
+  if (n_queries == 0) return MMRS_OK;
+  if (n_lists < 1 || n_queries < 0 || k_in < 1 || k_out < 1 || k_out > 1024 ||
+      static_cast<int64_t>(n_lists) * k_in < k_out)
+    return fail(MMRS_ERR_ARG, "bad merge shape: %d lists x %d, k_out %d", n_lists, k_in, k_out);
+  if (!d_keys_in || !d_out_values || !d_out_indices) return fail(MMRS_ERR_ARG, "null pointer");
+  MMRS_CUDA(cudaMemsetAsync(d_status, 0, sizeof(int32_t), stream));
+  SelectParams sp{};
+  sp.cand = const_cast<uint64_t*>(d_keys_in);
+  sp.cap = n_lists * k_in; sp.fixed_n = n_lists * k_in; sp.k = k_out; sp.final_pass = 1;
+  sp.out_values = d_out_values; sp.out_indices = d_out_indices; sp.index_offset = 0; sp.flags = d_status;
+  if (list_stride < static_cast<int64_t>(n_queries) * k_in) return fail(MMRS_ERR_ARG, "list_stride too small");
+  sp.seg_len = k_in; sp.seg_stride = list_stride;
+  MMRS_LAUNCH(launch_select(sp, n_queries, stream));
+  MMRS_CUDA(cudaMemcpyAsync(h_status, d_status, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  return MMRS_OK;
 }
 
 int mmrs_search_status(const int32_t* h_status) {

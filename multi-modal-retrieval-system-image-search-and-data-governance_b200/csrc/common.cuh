@@ -131,6 +131,11 @@ struct SelectParams {
   int64_t* out_indices;   // [n_queries, k]
   int64_t index_offset;
   int32_t* flags;
+  uint64_t* out_keys;     // final pass, optional: [n_queries, k] keys with GLOBAL rows (row + index_offset)
+  // segmented input (merge of all-gathered lists laid out [n_lists, n_queries, seg_len]):
+  // element i of query q's list lives at cand[(i / seg_len) * seg_stride + q * seg_len + i % seg_len]
+  int32_t seg_len;        // 0 = plain [n_queries, cap] layout
+  int64_t seg_stride;
 };
 
 // launchers (defined in the .cu files, called from api.cu)

@@ -70,12 +70,18 @@ __device__ __forceinline__ void select_body(const SelectParams& p, SelShared& sh
   constexpr bool in_regs = KPT > 0;
   constexpr int R = in_regs ? KPT : 1;
 
+  const int32_t seg_len = p.seg_len;
+  const uint64_t* seg_base = p.cand + static_cast<int64_t>(q) * seg_len;
+  auto load = [&](uint32_t idx) -> uint64_t {
+    if (seg_len == 0) return list[idx];
+    return seg_base[static_cast<int64_t>(idx / seg_len) * p.seg_stride + idx % seg_len];
+  };
   uint64_t key[R];
   if constexpr (in_regs) {
 #pragma unroll
     for (int i = 0; i < KPT; ++i) {
       const uint32_t idx = tid + i * kSelThreads;
-      key[i] = idx < n ? list[idx] : 0ull;   // 0 is below every real key
+      key[i] = idx < n ? load(idx) : 0ull;   // 0 is below every real key
     }
   }
   auto for_each_key = [&](auto&& f) {
@@ -86,7 +92,7 @@ __device__ __forceinline__ void select_body(const SelectParams& p, SelShared& sh
       // block-uniform trip count (the callbacks use warp collectives); 0 pads the tail
       for (uint32_t base = 0; base < n; base += kSelThreads) {
         const uint32_t idx = base + tid;
-        f(idx < n ? list[idx] : 0ull);
+        f(idx < n ? load(idx) : 0ull);
       }
     }
   };
@@ -239,8 +245,12 @@ __device__ __forceinline__ void select_body(const SelectParams& p, SelShared& sh
       const uint64_t mine = sh.winners[i];
       uint32_t rank = 0;
       for (uint32_t j = 0; j < n_win; ++j) rank += sh.winners[j] > mine;
-      p.out_values[static_cast<int64_t>(q) * k + rank] = key_score(mine);
-      p.out_indices[static_cast<int64_t>(q) * k + rank] = static_cast<int64_t>(key_row(mine)) + p.index_offset;
+      const int64_t grow = static_cast<int64_t>(key_row(mine)) + p.index_offset;
+      if (p.out_values) p.out_values[static_cast<int64_t>(q) * k + rank] = key_score(mine);
+      if (p.out_indices) p.out_indices[static_cast<int64_t>(q) * k + rank] = grow;
+      if (p.out_keys)
+        p.out_keys[static_cast<int64_t>(q) * k + rank] =
+            (mine & 0xffffffff00000000ull) | static_cast<uint64_t>(~static_cast<uint32_t>(grow));
     }
   } else {
     // next list = the winners (unsorted); bound = score part of the pivot (<= every winner's score)

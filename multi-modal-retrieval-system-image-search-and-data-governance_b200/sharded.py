@@ -77,6 +77,17 @@ def _merge_cuda(values: torch.Tensor, indices: torch.Tensor, k: int):
     return out_v, out_i
 
 
+class _PendingSharded:
+    def __init__(self, finish, general):
+        self._finish, self._general, self._out = finish, general, None
+
+    def wait(self):
+        if self._out is None:
+            out = self._finish()
+            self._out = out if out is not None else self._general()
+        return self._out
+
+
 class ShardedGallery:
     """This rank's shard of a row-sharded gallery plus the merge step.
 
@@ -92,6 +103,7 @@ class ShardedGallery:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self._fast = local_search is None and merge is None   # product path: packed-key pipeline
         if local_search is None:
             from .search import search_topk as local_search
         self._search = local_search
@@ -107,13 +119,99 @@ class ShardedGallery:
         local = DeviceGallery(features[lo:hi], mode=mode, device=device, row_offset=lo)
         return cls(local, features.shape[0], group)
 
+    def _search_topk_keys(self, queries, k: int, normalize_queries: bool, scale: float, path: str):
+        """CUDA fast path: local top-k as packed 64-bit keys -> ONE all-gather (Q*k*8 bytes per rank)
+        -> merge kernel reading the gathered buffer in place.  Nothing synchronises with the host
+        until the final status check."""
+        from .search import _prep_queries
+        gal = self.local
+        q, on_host = _prep_queries(queries, gal)
+        if on_host:
+            q = q.to(gal.device, non_blocking=True)
+        nq = int(q.shape[0])
+        dev = gal.device
+        lib = _cabi.lib
+        if torch.cuda.current_device() != dev.index:
+            torch.cuda.set_device(dev)
+        k_local = min(k, gal.n_rows)
+        n_keys = nq * k
+        buf = torch.zeros(n_keys + 1, dtype=torch.int64, device=dev)      # key 0 = "no entry"; [-1] = status
+        status = torch.zeros(2, dtype=torch.int32).pin_memory()
+        stream = torch.cuda.current_stream(dev)
+        ws_ptr, ws_bytes = gal.search_workspace(nq, k_local, False)
+        if nq:
+            dst = buf if k_local == k else torch.empty(nq * k_local + 1, dtype=torch.int64, device=dev)
+            _cabi.check(lib.mmrs_search_topk_keys_async(
+                gal.data.data_ptr(), gal.n_rows, gal.padded_dim, gal.data.stride(0), gal.dtype_code,
+                q.data_ptr(), nq, q.stride(0), k_local, int(bool(normalize_queries)), float(scale),
+                gal.row_offset, _cabi.PATHS[path], dst.data_ptr(), ws_ptr, ws_bytes, status.data_ptr(),
+                stream.cuda_stream))
+            if dst is not buf:                       # a shard shorter than k: pad its lists with key 0
+                buf[:n_keys].view(nq, k)[:, :k_local] = dst[:-1].view(nq, k_local)
+                buf[-1] = dst[-1]
+        gathered = _all_gather(buf, self.world, self.group)               # [world, nq*k + 1]
+        out_v = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        out_i = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        if nq:
+            d_status = torch.empty(1, dtype=torch.int32, device=dev)
+            _cabi.check(lib.mmrs_topk_merge_keys_async(gathered.data_ptr(), self.world, nq, k, n_keys + 1, k,
+                                                       out_v.data_ptr(), out_i.data_ptr(), d_status.data_ptr(),
+                                                       status[1:].data_ptr(), stream.cuda_stream))
+            shard_status = gathered[:, -1].to("cpu", non_blocking=True)
+        else:
+            shard_status = None
+        if on_host:
+            hv = torch.empty((nq, k), dtype=torch.float32, pin_memory=True)
+            hi = torch.empty((nq, k), dtype=torch.int64, pin_memory=True)
+            hv.copy_(out_v, non_blocking=True)
+            hi.copy_(out_i, non_blocking=True)
+            out_v, out_i = hv, hi
+        event = torch.cuda.Event()
+        event.record(stream)
+
+        def finish():
+            event.synchronize()
+            if shard_status is None:
+                return out_v, out_i
+            worst = int(shard_status.max().item())
+            if worst == 1:
+                return None                          # some rank overflowed: ALL ranks take the general path
+            if worst != 0:                           # e.g. a zero-norm query: same error as single-GPU
+                status[0] = worst
+                _cabi.check(lib.mmrs_search_status(status.data_ptr()))
+            _cabi.check(lib.mmrs_search_status(status[1:].data_ptr()))
+            return out_v, out_i
+
+        finish._keepalive = (q, buf, gathered)
+        return finish
+
     def search_topk(self, queries: torch.Tensor, k: int, *, normalize_queries: bool = True,
-                    scale: float = 1.0, path: str = "auto"):
-        """Global top-k, identical on every rank.  `queries` must be the same on all ranks."""
-        n_local = len(self.local)
-        k_local = min(k, n_local)
+                    scale: float = 1.0, path: str = "auto", sync: bool = True):
+        """Global top-k, identical on every rank.  `queries` must be the same on all ranks.
+        `sync=False` returns an object whose `.wait()` yields `(values, indices)`, so that several
+        batches (and their all-gathers) can be in flight."""
         if k > self.n_rows_global:
             raise RuntimeError("selected index k out of range")
+        if self._fast and self.world > 1:
+            finish = self._search_topk_keys(queries, k, normalize_queries, scale, path)
+            general = lambda: self.search_topk_general(queries, k, normalize_queries=normalize_queries,
+                                                       scale=scale, path=path)
+            pend = _PendingSharded(finish, general)
+            return pend.wait() if sync else pend
+        out = self.search_topk_general(queries, k, normalize_queries=normalize_queries, scale=scale, path=path)
+        return out if sync else _PendingSharded(lambda: out, None)
+
+    def search_topk_general(self, queries: torch.Tensor, k: int, *, normalize_queries: bool = True,
+                            scale: float = 1.0, path: str = "auto"):
+        """(values, indices) lists, two all-gathers, merge -- also the path every rank takes together
+        when some rank's candidate list overflowed (None from the fast path on EVERY rank alike: the
+        shard statuses were gathered with the keys)."""
+        n_local = len(self.local)
+        k_local = min(k, n_local)
+        on_host = False
+        if self._fast and self.world > 1 and not (isinstance(queries, torch.Tensor) and queries.is_cuda):
+            on_host = True                    # NCCL gathers device tensors: search on the device, copy back
+            queries = torch.as_tensor(queries).to(self.local.device)
         v, i = self._search(queries, self.local, k_local, normalize_queries=normalize_queries,
                             scale=scale, path=path)
         if self.world == 1:
@@ -125,7 +223,8 @@ class ShardedGallery:
             i = torch.cat([i, torch.full((i.shape[0], pad), 2 ** 32 - 1, dtype=i.dtype, device=i.device)], 1)
         gv = _all_gather(v, self.world, self.group)
         gi = _all_gather(i, self.world, self.group)
-        return self._merge(gv, gi, k)
+        mv, mi = self._merge(gv, gi, k)
+        return (mv.cpu(), mi.cpu()) if on_host else (mv, mi)
 
     def find_duplicate_pairs(self, emb_full: torch.Tensor, threshold: float, raw_join: Optional[Callable] = None):
         """Self-join with the gallery replicated (10M x 512 fp32 = 20 GB fits every GPU) and the

@@ -22,6 +22,30 @@ for nq in (3, 24):
     bad = (i.cpu() != wi).sum().item()
     assert bad <= 2, (rank, nq, bad)
     assert (v.cpu() - wv).abs().max().item() < 1e-5
+# host queries in -> host results out; asynchronous handle
+q = oracle.synthetic_queries(5, d, seed=9)
+pend = sg.search_topk(q, k, sync=False)
+hv, hi = pend.wait()
+wv, wi = oracle.search_topk(q, g, k, mode="bf16")
+assert not hv.is_cuda and (hi != wi).sum().item() <= 1
+# a candidate-list overflow on ONE rank: every rank must fall back to the general path together
+n2 = 140_032
+g2 = oracle.synthetic_gallery(n2, 32, seed=5, dtype=torch.float32)
+q2 = oracle.synthetic_queries(2, 32)
+tiles = torch.arange(n2) // 128
+hot = (tiles % 16 != 0) & (torch.arange(n2) < 70_016)          # rank 0's shard, outside its seed sample
+g2[hot] = oracle.l2_normalize(g2[hot] + 2.0 * oracle.l2_normalize(q2)[0])
+sg2 = mmrs_b200.ShardedGallery.from_full(g2, device=dev)
+v2, i2 = sg2.search_topk(q2.to(dev), 10)
+wv2, wi2 = oracle.search_topk(q2, g2, 10)
+assert torch.equal(i2.cpu(), wi2), (rank, i2, wi2)
+# zero-norm query: same error on every rank
+qz = oracle.synthetic_queries(3, d); qz[1] = 0
+try:
+    sg.search_topk(qz.to(dev), k)
+    raise SystemExit("zero-norm query was accepted")
+except mmrs_b200._cabi.MmrsError as e:
+    assert e.code == mmrs_b200._cabi.ERR_ZERO_NORM
 x, planted = oracle.synthetic_dedup(30_000, 128, dup_frac=0.02, seed=5)
 pairs = sg.find_duplicate_pairs(mmrs_b200.dedup._device_f32(x, dev), 0.95)
 assert [tuple(p) for p in pairs.cpu().tolist()] == planted
