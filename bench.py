@@ -306,9 +306,16 @@ def main():
         avg_ms = sum(r[0] for r in dom) / len(dom)
         achieved = big / (avg_ms / 1e3) / 1e9
         scan_ms_per_step = sum(r[0] for r in recs) / args.steps
+        kname = "scan_mma_kernel<filter>" if dom[0][1] == 2 else "scan_gemv_kernel<filter>"
+        traffic = None
+        tpath = ROOT / "profiles" / "traffic.json"      # dram__bytes_read+write of one ncu --set full capture
+        if tpath.exists() and args.rows == ROWS_PER_GPU and args.dim == DIM:
+            tj = json.loads(tpath.read_text()).get(kname)
+            if tj:
+                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
         roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "traffic": None, "peak_source": f"{peak_src} (MEASURED_PEAKS.json hbm_gbs, burst copy)",
-                    "kernel": "scan_mma_kernel<filter>" if dom[0][1] == 2 else "scan_gemv_kernel<filter>",
+                    "traffic": traffic, "peak_source": f"{peak_src} (MEASURED_PEAKS.json hbm_gbs, burst copy)",
+                    "kernel": kname,
                     "algorithmic_bytes_per_launch": big, "avg_launch_ms": avg_ms, "launches_timed": len(dom),
                     "tflops": dom[0][3] / (avg_ms / 1e3) / 1e12,
                     "scan_kernels_ms_per_step": scan_ms_per_step, "share_of_step": scan_ms_per_step / (ms_total / args.steps),

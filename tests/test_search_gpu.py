@@ -273,3 +273,63 @@ def test_clustered_gallery_grouped_by_class(mm, oracle):
     q = centers[9:10] + 0.1 * torch.randn(12, 256, generator=gen)
     check_bf16(mm, oracle, g, q, 100, "auto")
     check_bf16(mm, oracle, g, q[:3], 100, "gemv")
+
+
+# ---- larger-than-oracle sizes: a torch-on-GPU reference (test infrastructure only) -----------------
+def torch_gpu_topk(q, gal_data, k, block=1 << 20):
+    """fp32 matmul of the same bf16-valued operands on the GPU, blocked over rows, stable order."""
+    qn = (q / q.norm(dim=-1, keepdim=True)).to(torch.bfloat16).to(torch.float32).cuda()
+    best_v = best_i = None
+    for lo in range(0, gal_data.shape[0], block):
+        s = qn @ gal_data[lo:lo + block].to(torch.float32).t()
+        v, i = torch.sort(s, dim=1, descending=True, stable=True)
+        v, i = v[:, :k], i[:, :k] + lo
+        if best_v is None:
+            best_v, best_i = v, i
+        else:
+            cv, ci = torch.cat([best_v, v], 1), torch.cat([best_i, i], 1)
+            o = torch.sort(cv, dim=1, descending=True, stable=True)[1][:, :k]
+            best_v, best_i = torch.gather(cv, 1, o), torch.gather(ci, 1, o)
+    return best_v.cpu(), best_i.cpu()
+
+
+def test_c4_shard_size_12p5m_x_768(mm):
+    """One GPU's share of C4 (100M x 768 over 8 GPUs = 12.5M rows, 19.2 GB): 4-phase plan."""
+    from bench import device_gallery_shard
+    dev = torch.device("cuda", 0)
+    data = device_gallery_shard(torch, 12_500_000, 768, 0, 0, dev)
+    gal = mm.DeviceGallery(data, row_offset=25_000_000)
+    q = torch.randn(16, 768, generator=torch.Generator().manual_seed(3))
+    v, i = mm.search_topk(q, gal, 100)
+    wv, wi = torch_gpu_topk(q, data, 100)
+    np.testing.assert_allclose(v.numpy(), wv.numpy(), atol=2e-6, rtol=0)
+    assert explain_index_mismatches(i.numpy() - 25_000_000, wi.numpy(), wv.numpy(), 2e-6) <= 8
+    v1, i1 = mm.search_topk(q[:2], gal, 100, path="gemv")
+    assert (i1 == i[:2]).float().mean().item() > 0.99
+    del gal, data
+    torch.cuda.empty_cache()
+
+
+def test_many_queries_super_chunks(mm, oracle):
+    """2 500 queries: more than one 1024-query super-chunk and ten 256-query K2 passes."""
+    g = oracle.synthetic_gallery(120_000, 128, seed=12, dtype=torch.bfloat16)
+    q = oracle.synthetic_queries(2500, 128, seed=13)
+    v, i = mm.search_topk(q.cuda(), mm.DeviceGallery(g), 10)
+    wv, wi = torch_gpu_topk(q, g.cuda(), 10)
+    np.testing.assert_allclose(v.cpu().numpy(), wv.numpy(), atol=2e-6, rtol=0)
+    assert explain_index_mismatches(i.cpu().numpy(), wi.numpy(), wv.numpy(), 2e-6) <= 25
+    ov, oi = oracle.search_topk(q[:64], g, 10, mode="bf16")
+    assert explain_index_mismatches(i[:64].cpu().numpy(), oi.numpy(), ov.numpy(), 2e-6) <= 2
+
+
+def test_async_search_handles(mm, oracle):
+    g = oracle.synthetic_gallery(100_000, 256, seed=14, dtype=torch.bfloat16)
+    gal = mm.DeviceGallery(g)
+    qs = [oracle.synthetic_queries(8, 256, seed=s) for s in range(4)]
+    pend = [mm.search_topk(q, gal, 20, sync=False) for q in qs]          # four host batches in flight
+    for q, pnd in zip(qs, pend):
+        v, i = pnd.wait()
+        wv, wi = mm.search_topk(q, gal, 20)
+        assert torch.equal(i, wi) and torch.equal(v, wv)
+    pd = mm.search_topk(qs[0].cuda(), gal, 20, sync=False)
+    assert torch.equal(pd.wait()[1].cpu(), pend[0].wait()[1])
