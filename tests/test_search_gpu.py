@@ -212,7 +212,26 @@ def test_full_size_c2_small_batch(mm, oracle, nq):
 
 
 # ---- K2 (tcgen05) explicitly -----------------------------------------------------------------------
+def bf16_unit_queries(q):
+    """Normalise and round to bf16 ONCE on the host.  Strict comparisons feed these to both sides with
+    normalize_queries=False: rounding the normalised query to bf16 is discontinuous, so two
+    implementations whose fp32 norms differ in the last ulp flip a bf16 query element about once
+    per 1e5 elements, which moves that query's scores by ~1e-4 (seen at 2 500 x 128 queries) --
+    inside north_star's 1e-2, far outside a 1e-5 check."""
+    return (q / q.norm(dim=-1, keepdim=True)).to(torch.bfloat16).to(torch.float32)
+
+
 def check_bf16(mm, oracle, g, q, k, path, **kw):
+    if kw.get("normalize_queries", True):
+        # fused normalisation: north_star's own tolerances (scores 1e-2, recall@k 0.999) ...
+        lv, li = mm.search_topk(q, mm.DeviceGallery(g), k, path=path, **kw)
+        ov, oi = oracle.search_topk(q, g, k, mode="bf16", **kw)
+        np.testing.assert_allclose(lv.cpu().numpy(), ov.numpy(), atol=1e-2, rtol=0)
+        hits = sum(len(set(a) & set(b)) for a, b in zip(li.cpu().tolist(), oi.tolist()))
+        assert hits / oi.numel() >= 0.999
+        # ... then the strict comparison on identical bf16-valued operands
+        q = bf16_unit_queries(q)
+        kw = dict(kw, normalize_queries=False)
     want_v, want_i = oracle.search_topk(q, g, k, mode="bf16", **kw)
     v, i = mm.search_topk(q, mm.DeviceGallery(g), k, path=path, **kw)
     v, i = v.cpu().numpy(), i.cpu().numpy()
@@ -276,9 +295,10 @@ def test_clustered_gallery_grouped_by_class(mm, oracle):
 
 
 # ---- larger-than-oracle sizes: a torch-on-GPU reference (test infrastructure only) -----------------
-def torch_gpu_topk(q, gal_data, k, block=1 << 20):
-    """fp32 matmul of the same bf16-valued operands on the GPU, blocked over rows, stable order."""
-    qn = (q / q.norm(dim=-1, keepdim=True)).to(torch.bfloat16).to(torch.float32).cuda()
+def torch_gpu_topk(qn, gal_data, k, block=1 << 20):
+    """fp32 matmul of the same bf16-valued operands (qn = bf16_unit_queries) on the GPU, blocked over
+    rows, stable order."""
+    qn = qn.cuda()
     best_v = best_i = None
     for lo in range(0, gal_data.shape[0], block):
         s = qn @ gal_data[lo:lo + block].to(torch.float32).t()
@@ -299,12 +319,12 @@ def test_c4_shard_size_12p5m_x_768(mm):
     dev = torch.device("cuda", 0)
     data = device_gallery_shard(torch, 12_500_000, 768, 0, 0, dev)
     gal = mm.DeviceGallery(data, row_offset=25_000_000)
-    q = torch.randn(16, 768, generator=torch.Generator().manual_seed(3))
-    v, i = mm.search_topk(q, gal, 100)
+    q = bf16_unit_queries(torch.randn(16, 768, generator=torch.Generator().manual_seed(3)))
+    v, i = mm.search_topk(q, gal, 100, normalize_queries=False)
     wv, wi = torch_gpu_topk(q, data, 100)
     np.testing.assert_allclose(v.numpy(), wv.numpy(), atol=2e-6, rtol=0)
     assert explain_index_mismatches(i.numpy() - 25_000_000, wi.numpy(), wv.numpy(), 2e-6) <= 8
-    v1, i1 = mm.search_topk(q[:2], gal, 100, path="gemv")
+    v1, i1 = mm.search_topk(q[:2], gal, 100, path="gemv", normalize_queries=False)
     assert (i1 == i[:2]).float().mean().item() > 0.99
     del gal, data
     torch.cuda.empty_cache()
@@ -313,12 +333,12 @@ def test_c4_shard_size_12p5m_x_768(mm):
 def test_many_queries_super_chunks(mm, oracle):
     """2 500 queries: more than one 1024-query super-chunk and ten 256-query K2 passes."""
     g = oracle.synthetic_gallery(120_000, 128, seed=12, dtype=torch.bfloat16)
-    q = oracle.synthetic_queries(2500, 128, seed=13)
-    v, i = mm.search_topk(q.cuda(), mm.DeviceGallery(g), 10)
+    q = bf16_unit_queries(oracle.synthetic_queries(2500, 128, seed=13))
+    v, i = mm.search_topk(q.cuda(), mm.DeviceGallery(g), 10, normalize_queries=False)
     wv, wi = torch_gpu_topk(q, g.cuda(), 10)
     np.testing.assert_allclose(v.cpu().numpy(), wv.numpy(), atol=2e-6, rtol=0)
     assert explain_index_mismatches(i.cpu().numpy(), wi.numpy(), wv.numpy(), 2e-6) <= 25
-    ov, oi = oracle.search_topk(q[:64], g, 10, mode="bf16")
+    ov, oi = oracle.search_topk(q[:64], g, 10, mode="bf16", normalize_queries=False)
     assert explain_index_mismatches(i[:64].cpu().numpy(), oi.numpy(), ov.numpy(), 2e-6) <= 2
 
 
