@@ -15,7 +15,7 @@
  *   mmrs_search_topk      code/search_image.py:107 + code/utils.py:17
  *                         `output.topk(k, 1, True, True)` fused, score matrix never stored
  *   mmrs_topk_merge       (new) merge of per-shard top-k after the all-gather
- *   mmrs_selfjoin_pairs   tool/find_repeated_in_same_folder.py:76-95 /
+ *   mmrs_selfjoin_pairs(_tc)  tool/find_repeated_in_same_folder.py:76-95 /
  *                         tool/delete repeated.py:127-135 (pairwise join loop), with the
  *                         predicate cos(e_i, e_j) >= tau named by BASELINE.json
  *   mmrs_threshold_sweep  code/search_image.py:39-79 (eval_threshold / find_thresholds)
@@ -210,6 +210,24 @@ int mmrs_selfjoin_pairs(const void* d_emb, int64_t n_rows, int32_t dim, int64_t 
                         int32_t dtype, float threshold, int64_t row_begin, int64_t row_end,
                         int64_t* d_out_pairs, int64_t capacity, int64_t* d_out_count,
                         void* d_workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Tensor-core form of the same join: a bf16 tcgen05 pass over d_emb_bf16 (the same rows rounded to
+ * bf16) keeps pairs with <e_i, e_j> >= threshold - margin, and every survivor is re-scored in fp32
+ * from d_emb_f32 with the arithmetic of mmrs_selfjoin_pairs, so the emitted set is identical to
+ * the exact mode's provided margin covers the bf16 rounding (unit-norm rows: margin >= 0.004, see
+ * csrc/selfjoin_mma.cu).  The upper triangle is split into panels of 2048 columns dealt round-robin
+ * to `world` ranks; this call does rank `rank`'s share.  d_out_count is device int64[2]:
+ * [0] pairs found, [1] candidates that passed the prefilter; MMRS_ERR_CAPACITY when either exceeds
+ * its capacity (the counts are still reported so the caller can size a retry).
+ * Synchronises `stream`.
+ */
+size_t mmrs_selfjoin_tc_workspace_bytes(int64_t n_rows, int64_t cand_capacity);
+int mmrs_selfjoin_pairs_tc(const float* d_emb_f32, int64_t ld_f32, const void* d_emb_bf16,
+                           int64_t ld_bf16, int64_t n_rows, int32_t dim, float threshold,
+                           float margin, int32_t rank, int32_t world, int64_t* d_out_pairs,
+                           int64_t capacity, int64_t* d_out_count, int64_t cand_capacity,
+                           void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* ---- threshold / F1 sweep (the reference's consumer of the scores) ------------------ */
 

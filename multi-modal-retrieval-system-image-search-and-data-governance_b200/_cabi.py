@@ -64,6 +64,9 @@ SIGNATURES = {
     "mmrs_selfjoin_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "mmrs_selfjoin_pairs": (C.c_int, [_vp, _i64, _i32, _i64, _i32, _f32, _i64, _i64, _vp, _i64,
                                       _vp, _vp, _sz, _vp]),
+    "mmrs_selfjoin_tc_workspace_bytes": (_sz, [_i64, _i64]),
+    "mmrs_selfjoin_pairs_tc": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _f32, _f32, _i32, _i32, _vp, _i64,
+                                         _vp, _i64, _vp, _sz, _vp]),
     "mmrs_threshold_sweep_workspace_bytes": (_sz, [_i32]),
     "mmrs_launch_count": (_i64, []),
     "mmrs_profile_enable": (C.c_int, [C.c_int]),

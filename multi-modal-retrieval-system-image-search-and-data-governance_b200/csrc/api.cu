@@ -24,6 +24,18 @@ cudaError_t launch_selfjoin_f32(const float* emb, int64_t n_rows, int32_t dim, i
 cudaError_t launch_threshold_sweep(const float* pos, int64_t n_pos, const float* neg, int64_t n_neg,
                                    const double* thr, int32_t n_thr, int64_t* out_counts,
                                    unsigned long long* hist_ws, int sm_count, cudaStream_t stream);
+// K5 on tensor cores (selfjoin_mma.cu)
+int64_t sjm_plan(int64_t n_rows, int32_t rank, int32_t world, int64_t* h_panel_start, int32_t max_panels,
+                 int32_t* n_my_panels);
+int64_t sjm_max_panels(int64_t n_rows);
+cudaError_t launch_selfjoin_mma(const __nv_bfloat16* emb16, int64_t n_rows, int32_t dim, int64_t ld16,
+                                float thr_lo, int32_t rank, int32_t world, const int64_t* d_panel_start,
+                                int32_t n_my_panels, int64_t total_tiles, int64_t* cand, int64_t cand_cap,
+                                unsigned long long* cand_count, int32_t* flags, int sm_count,
+                                cudaStream_t stream);
+cudaError_t launch_selfjoin_recheck(const int64_t* cand, int64_t n_cand, const float* emb, int64_t ld, int32_t dim,
+                                    float threshold, int64_t* out_pairs, int64_t capacity,
+                                    unsigned long long* out_count, cudaStream_t stream);
 // K2.  q_bf16 is the prepared [n_q_padded, ldq] bf16 query matrix; handles up to 256 queries.
 cudaError_t launch_scan_mma(const ScanParams& p, const __nv_bfloat16* q_bf16, int32_t n_q_padded,
                             int mode, int32_t* flags, int sm_count, cudaStream_t stream);
@@ -838,6 +850,73 @@ int mmrs_profile_read(float* h_ms, int32_t* h_kind, int64_t* h_bytes, int64_t* h
   }
   g_prof.clear();
   return n;
+}
+
+size_t mmrs_selfjoin_tc_workspace_bytes(int64_t n_rows, int64_t cand_capacity) {
+  if (n_rows < 1) n_rows = 1;
+  if (cand_capacity < 1) cand_capacity = 1;
+  return 512 + align_up(static_cast<size_t>(sjm_max_panels(n_rows) + 1) * sizeof(int64_t), 256) +
+         align_up(static_cast<size_t>(cand_capacity) * 2 * sizeof(int64_t), 256);
+}
+
+int mmrs_selfjoin_pairs_tc(const float* d_emb_f32, int64_t ld_f32, const void* d_emb_bf16, int64_t ld_bf16,
+                           int64_t n_rows, int32_t dim, float threshold, float margin, int32_t rank,
+                           int32_t world, int64_t* d_out_pairs, int64_t capacity, int64_t* d_out_count,
+                           int64_t cand_capacity, void* d_workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceInfo dev;
+  int rc = current_device(&dev);
+  if (rc != MMRS_OK) return rc;
+  rc = check_matrix(d_emb_f32, n_rows, dim, ld_f32, MMRS_DTYPE_F32, "fp32 embeddings");
+  if (rc != MMRS_OK) return rc;
+  rc = check_matrix(d_emb_bf16, n_rows, dim, ld_bf16, MMRS_DTYPE_BF16, "bf16 embeddings");
+  if (rc != MMRS_OK) return rc;
+  if (!(margin >= 0.f) || world < 1 || rank < 0 || rank >= world)
+    return fail(MMRS_ERR_ARG, "bad margin / rank / world");
+  if (capacity < 0 || cand_capacity < 1 || (capacity > 0 && !d_out_pairs) || !d_out_count)
+    return fail(MMRS_ERR_ARG, "bad output arguments");
+  const size_t need = mmrs_selfjoin_tc_workspace_bytes(n_rows, cand_capacity);
+  if (!d_workspace || workspace_bytes < need || reinterpret_cast<uintptr_t>(d_workspace) % 256)
+    return fail(MMRS_ERR_WORKSPACE, "workspace %zu bytes, need %zu (256-byte aligned)", workspace_bytes, need);
+  char* b = static_cast<char*>(d_workspace);
+  int32_t* flags = reinterpret_cast<int32_t*>(b);
+  unsigned long long* counts = reinterpret_cast<unsigned long long*>(b + 256);   // [0] pairs, [1] candidates
+  int64_t* d_panel = reinterpret_cast<int64_t*>(b + 512);
+  const int64_t max_panels = sjm_max_panels(n_rows);
+  int64_t* cand = reinterpret_cast<int64_t*>(b + 512 + align_up(static_cast<size_t>(max_panels + 1) * sizeof(int64_t), 256));
+
+  std::vector<int64_t> h_panel(static_cast<size_t>(max_panels) + 1);
+  int32_t n_my = 0;
+  const int64_t tiles = sjm_plan(n_rows, rank, world, h_panel.data(), static_cast<int32_t>(max_panels), &n_my);
+  MMRS_CUDA(cudaMemsetAsync(b, 0, 512, stream));
+  MMRS_CUDA(cudaMemcpyAsync(d_panel, h_panel.data(), static_cast<size_t>(n_my + 1) * sizeof(int64_t),
+                            cudaMemcpyHostToDevice, stream));
+  MMRS_CUDA(cudaStreamSynchronize(stream));   // h_panel is pageable and goes out of scope
+  MMRS_LAUNCH(launch_selfjoin_mma(static_cast<const __nv_bfloat16*>(d_emb_bf16), n_rows, dim, ld_bf16,
+                                  threshold - margin, rank, world, d_panel, n_my, tiles, cand, cand_capacity,
+                                  counts + 1, flags, dev.sm_count, stream));
+  int32_t* h = pinned_status();
+  if (!h) return fail(MMRS_ERR_CUDA, "cudaHostAlloc for the status word failed");
+  int64_t* h64 = reinterpret_cast<int64_t*>(h);      // 32 bytes: [0] pairs, [1] candidates, [2] flags
+  MMRS_CUDA(cudaMemcpyAsync(h64 + 1, counts + 1, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+  MMRS_CUDA(cudaMemcpyAsync(h64 + 2, flags, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  MMRS_CUDA(cudaStreamSynchronize(stream));
+  if (h[4] & kFlagWatchdog) return fail(MMRS_ERR_INTERNAL, "self-join pipeline watchdog fired");
+  const int64_t n_cand = h64[1];
+  h64[0] = 0;
+  if (n_cand <= cand_capacity) {
+    MMRS_LAUNCH(launch_selfjoin_recheck(cand, n_cand, d_emb_f32, ld_f32, dim, threshold, d_out_pairs, capacity,
+                                        counts, stream));
+    MMRS_CUDA(cudaMemcpyAsync(h64, counts, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+  }
+  MMRS_CUDA(cudaMemcpyAsync(d_out_count, counts, 2 * sizeof(int64_t), cudaMemcpyDeviceToDevice, stream));
+  MMRS_CUDA(cudaStreamSynchronize(stream));
+  if (n_cand > cand_capacity)
+    return fail(MMRS_ERR_CAPACITY, "%lld candidate pairs, candidate capacity %lld", (long long)n_cand,
+                (long long)cand_capacity);
+  if (h64[0] > capacity)
+    return fail(MMRS_ERR_CAPACITY, "%lld pairs found, capacity %lld", (long long)h64[0], (long long)capacity);
+  return MMRS_OK;
 }
 
 size_t mmrs_threshold_sweep_workspace_bytes(int32_t n_thresholds) {

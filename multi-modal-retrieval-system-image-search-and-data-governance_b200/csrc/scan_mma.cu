@@ -16,9 +16,7 @@
 // The accumulator is double buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
 // Roofline: HBM-bound (N*D*2 bytes per pass) up to Q ~ 200, tensor-bound beyond
 // (SURVEY.md section 8d).
-#include <cuda.h>
-
-#include "common.cuh"
+#include "tcgen05_utils.cuh"
 
 namespace mmrs {
 
@@ -29,7 +27,6 @@ constexpr int kUmmaK = 16;
 constexpr int kMaxQ = 256;               // UMMA N limit
 constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KiB
 constexpr int kMaxStages = 8;
-constexpr uint32_t kWatchdogSpins = 1u << 24;
 constexpr uint32_t kStash = 8;            // parked candidates per epilogue thread before a flush
 
 struct MmaShared {
@@ -51,97 +48,6 @@ struct MmaCfg {
   int32_t acc_stride;    // column offset between the two accumulator stages
 };
 
-// ---- PTX wrappers ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a pipeline bug must end the kernel with a status flag, not hang the GPU.
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, MmaShared* sh, int32_t* flags) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (sh->abort) return false;
-    if (++spins > kWatchdogSpins) {
-      sh->abort = 1;
-      atomicOr(flags, kFlagWatchdog);
-      return false;
-    }
-  }
-  return true;
-}
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
-                                            int32_t c0, int32_t c1, uint64_t cache_hint) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-      " [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0),
-      "r"(c1), "l"(cache_hint)
-      : "memory");
-}
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// 32 lanes x 16 consecutive fp32 columns: thread i of the warp gets TMEM lane (base + i)
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"): rows are 128 bytes,
-// 8-row core groups are 1024 bytes apart (SBO); LBO is unused for swizzled K-major layouts.
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3ffffu) >> 4);       // start address, bits [0,14)
-  d |= static_cast<uint64_t>(1) << 16;                           // leading byte offset (>>4), unused
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;                   // stride byte offset (>>4)
-  d |= static_cast<uint64_t>(1) << 46;                           // descriptor version (Blackwell)
-  d |= static_cast<uint64_t>(2) << 61;                           // layout type: SWIZZLE_128B
-  return d;
-}
-// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M=128, N=n.
-__host__ __device__ constexpr uint32_t make_idesc(uint32_t n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((kBlockM >> 4) << 24);
-}
-
-constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;   // gallery: streamed once
-constexpr uint64_t kEvictLast = 0x14F0000000000000ull;    // queries: re-read by every tile
 
 template <int MODE>
 __global__ void __launch_bounds__(kMmaThreads, 1)
@@ -195,7 +101,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
         if (exc != 0 && (t % exc) == 0) continue;
         const int32_t row0 = t * kBlockM;
         for (int kb = 0; kb < cfg.k_blocks; ++kb) {
-          if (!mbar_wait(&sh->empty[stage], phase ^ 1, sh, flags)) { ok = false; break; }
+          if (!mbar_wait(&sh->empty[stage], phase ^ 1, &sh->abort, flags)) { ok = false; break; }
           uint8_t* a_dst = ring + static_cast<size_t>(stage) * stage_bytes;
           mbar_expect_tx(&sh->full[stage], stage_bytes);
           tma_load_2d(a_dst, &map_g, &sh->full[stage], kb * kBlockK, row0, kEvictFirst);
@@ -214,11 +120,11 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
         const int t = j * inc;
         if (exc != 0 && (t % exc) == 0) continue;
         const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-        if (!mbar_wait(&sh->tmem_empty[as], aphase ^ 1, sh, flags)) break;
+        if (!mbar_wait(&sh->tmem_empty[as], aphase ^ 1, &sh->abort, flags)) break;
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + as * static_cast<uint32_t>(cfg.acc_stride);
         for (int kb = 0; kb < cfg.k_blocks; ++kb) {
-          if (!mbar_wait(&sh->full[stage], phase, sh, flags)) { ok = false; break; }
+          if (!mbar_wait(&sh->full[stage], phase, &sh->abort, flags)) { ok = false; break; }
           tcgen05_fence_after();
           const uint32_t a_addr = smem_u32(ring + static_cast<size_t>(stage) * stage_bytes);
           const uint64_t adesc = make_sw128_desc(a_addr);
@@ -248,7 +154,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
       const int t = j * inc;
       if (exc != 0 && (t % exc) == 0) continue;
       const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-      if (!mbar_wait(&sh->tmem_full[as], aphase, sh, flags)) break;
+      if (!mbar_wait(&sh->tmem_full[as], aphase, &sh->abort, flags)) break;
       tcgen05_fence_after();
       const int64_t row = static_cast<int64_t>(t) * kBlockM + r_in_tile;
       const bool row_ok = row <= last_row;
@@ -356,38 +262,6 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
                  "r"(static_cast<uint32_t>(cfg.tmem_cols))
                  : "memory");
   }
-}
-
-// ---- host side ---------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
-                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                  CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
-// 2-D bf16 row-major [rows, cols] tensor with row stride ld (elements); box = [box_rows, 64 cols]
-static bool make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
-                     uint32_t box_rows) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) return false;
-  cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld * 2};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 int scan_mma_max_queries() { return kMaxQ; }

@@ -1,0 +1,288 @@
+// selfjoin_mma.cu -- K5 on tensor cores: bf16 tcgen05 prefilter + exact fp32 recheck.
+//
+// N(N-1)/2 dot products is a GEMM (5.0e13 pairs at N = 10 M), so the
+// candidate pass runs on the 5th-gen tensor cores over a bf16 copy of the unit-norm embeddings:
+//   S[128 rows i, 256 rows j] = X16[i-block] * X16[j-block]^T      (tcgen05.mma, M=128, N=256)
+// and the epilogue keeps pairs (i < j) with S >= tau - margin.  Rounding unit rows to bf16 moves a
+// dot product by at most ||a|| ||b - b^|| + ||a - a^|| ||b^|| <= 2 * 2^-9 (1 + 2^-9) < 0.004
+// (Cauchy-Schwarz; round-to-nearest is within 2^-9 relative per element), so with margin >= 0.004
+// every true pair survives; the few survivors are then re-scored in fp32 with exactly the
+// arithmetic of the exact kernel (selfjoin.cu: one fmaf chain, k ascending), which makes the
+// emitted pair set identical to the exact mode's.
+//
+// Schedule: the upper triangle is cut into panels of 8 j-blocks (2048 rows: 2 MB of bf16 at
+// D = 512, L2 resident); inside a panel tiles are numbered j-fastest, so CTAs that run together
+// share their A rows and the B panel through L2.  Panels are dealt round-robin to the ranks of a
+// multi-GPU run (work per panel grows linearly with its index, so cyclic dealing balances).
+#include "tcgen05_utils.cuh"
+
+namespace mmrs {
+
+constexpr int kSjmThreads = 256;
+constexpr int kSjmBM = 128;
+constexpr int kSjmBN = 256;
+constexpr int kSjmBK = 64;
+constexpr int kSjmStages = 4;
+constexpr int kSjmPanel = 8;   // j-blocks per panel
+constexpr int kSjmABytes = kSjmBM * kSjmBK * 2;
+constexpr int kSjmBBytes = kSjmBN * kSjmBK * 2;
+constexpr int kSjmStageBytes = kSjmABytes + kSjmBBytes;
+
+struct SjmShared {
+  uint64_t full[kSjmStages];
+  uint64_t empty[kSjmStages];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+  volatile uint32_t abort;
+};
+
+struct SjmParams {
+  int64_t n_rows;
+  int32_t k_blocks;
+  float thr_lo;                    // tau - margin
+  int64_t nbi, nbj;                // number of 128-row i-blocks / 256-row j-blocks
+  int32_t n_my_panels;             // panels dealt to this rank: panel_begin + m * panel_stride
+  int32_t panel_begin, panel_stride;
+  const int64_t* panel_start;      // [n_my_panels + 1] first tile number of each of my panels
+  int64_t total_tiles;
+  int64_t* cand;                   // [cand_cap, 2]
+  int64_t cand_cap;
+  unsigned long long* cand_count;
+};
+
+// tile number -> (i-block, j-block); returns false for tiles that lie entirely on/below the diagonal
+__device__ __forceinline__ bool sjm_decode(const SjmParams& p, int64_t t, int64_t& ib, int64_t& jb) {
+  int lo = 0, hi = p.n_my_panels;           // last m with panel_start[m] <= t
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (p.panel_start[mid] <= t) lo = mid; else hi = mid;
+  }
+  const int64_t panel = p.panel_begin + static_cast<int64_t>(lo) * p.panel_stride;
+  const int64_t u = t - p.panel_start[lo];
+  int64_t nj = p.nbj - panel * kSjmPanel;
+  if (nj > kSjmPanel) nj = kSjmPanel;
+  ib = u / nj;
+  jb = panel * kSjmPanel + u % nj;
+  return jb * kSjmBN + (kSjmBN - 1) > ib * kSjmBM;
+}
+
+__global__ void __launch_bounds__(kSjmThreads, 1)
+selfjoin_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const SjmParams p, int32_t* flags) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  SjmShared* sh = reinterpret_cast<SjmShared*>(ring + kSjmStages * kSjmStageBytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kSjmStages; ++s) { mbar_init(&sh->full[s], 1); mbar_init(&sh->empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&sh->tmem_full[a], 1); mbar_init(&sh->tmem_empty[a], 4); }
+    sh->abort = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = sh->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {   // ===== TMA producer =====
+      uint32_t stage = 0, phase = 0;
+      bool ok = true;
+      for (int64_t t = blockIdx.x; t < p.total_tiles && ok; t += gridDim.x) {
+        int64_t ib, jb;
+        if (!sjm_decode(p, t, ib, jb)) continue;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          if (!mbar_wait(&sh->empty[stage], phase ^ 1, &sh->abort, flags)) { ok = false; break; }
+          uint8_t* a_dst = ring + static_cast<size_t>(stage) * kSjmStageBytes;
+          mbar_expect_tx(&sh->full[stage], kSjmStageBytes);
+          tma_load_2d(a_dst, &map_a, &sh->full[stage], kb * kSjmBK, static_cast<int32_t>(ib * kSjmBM), kEvictLast);
+          tma_load_2d(a_dst + kSjmABytes, &map_b, &sh->full[stage], kb * kSjmBK,
+                      static_cast<int32_t>(jb * kSjmBN), kEvictLast);
+          if (++stage == kSjmStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {   // ===== MMA issuer =====
+      const uint32_t idesc = make_idesc(kSjmBN);
+      uint32_t stage = 0, phase = 0, it = 0;
+      bool ok = true;
+      for (int64_t t = blockIdx.x; t < p.total_tiles && ok; t += gridDim.x) {
+        int64_t ib, jb;
+        if (!sjm_decode(p, t, ib, jb)) continue;
+        const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+        if (!mbar_wait(&sh->tmem_empty[as], aphase ^ 1, &sh->abort, flags)) break;
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + as * kSjmBN;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          if (!mbar_wait(&sh->full[stage], phase, &sh->abort, flags)) { ok = false; break; }
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(ring + static_cast<size_t>(stage) * kSjmStageBytes);
+          const uint64_t adesc = make_sw128_desc(a_addr);
+          const uint64_t bdesc = make_sw128_desc(a_addr + kSjmABytes);
+#pragma unroll
+          for (int k = 0; k < kSjmBK / 16; ++k)
+            umma_bf16(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
+                      (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&sh->empty[stage]);
+          if (++stage == kSjmStages) { stage = 0; phase ^= 1; }
+        }
+        if (ok) umma_commit(&sh->tmem_full[as]);
+        ++it;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: keep (i < j) with S >= tau - margin =====
+    const int ew = warp - 4;
+    uint32_t it = 0;
+    for (int64_t t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+      int64_t ib, jb;
+      if (!sjm_decode(p, t, ib, jb)) continue;
+      const uint32_t as = it & 1, aphase = (it >> 1) & 1;
+      if (!mbar_wait(&sh->tmem_full[as], aphase, &sh->abort, flags)) break;
+      tcgen05_fence_after();
+      const int64_t i = ib * kSjmBM + ew * 32 + lane;
+      const int64_t j0 = jb * kSjmBN;
+      const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * kSjmBN;
+      // columns at or left of the diagonal can never give j > i: skip whole chunks there
+      for (int c0 = 0; c0 < kSjmBN; c0 += 16) {
+        uint32_t acc[16];
+        __syncwarp();
+        tmem_ld16(taddr0 + static_cast<uint32_t>(c0), acc);
+        tmem_ld_wait();
+        uint32_t bits = 0;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) bits |= (__uint_as_float(acc[c]) >= p.thr_lo) ? (1u << c) : 0u;
+        while (bits) {
+          const int c = __ffs(bits) - 1;
+          bits &= bits - 1;
+          const int64_t j = j0 + c0 + c;
+          if (j > i && j < p.n_rows) {   // i < j < n_rows
+            const unsigned long long pos = atomicAdd(p.cand_count, 1ull);
+            if (pos < static_cast<unsigned long long>(p.cand_cap)) {
+              p.cand[2 * pos] = i;
+              p.cand[2 * pos + 1] = j;
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh->tmem_empty[as]);
+      ++it;
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  if (warp == 2)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
+// Exact fp32 re-score of the candidates: the same single fmaf chain, k ascending, as
+// selfjoin_f32_kernel, so both modes take bit-identical decisions.
+__global__ void __launch_bounds__(256) selfjoin_recheck_kernel(const int64_t* __restrict__ cand, int64_t n_cand,
+                                                               const float* __restrict__ emb, int64_t ld, int32_t dim,
+                                                               float threshold, int64_t* __restrict__ out_pairs,
+                                                               int64_t capacity, unsigned long long* out_count) {
+  const int64_t c = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (c >= n_cand) return;
+  const int64_t i = cand[2 * c], j = cand[2 * c + 1];
+  const float4* a = reinterpret_cast<const float4*>(emb + i * ld);
+  const float4* b = reinterpret_cast<const float4*>(emb + j * ld);
+  float acc = 0.f;
+  for (int k = 0; k < dim / 4; ++k) {
+    const float4 x = a[k], y = b[k];
+    acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc);
+    acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+  }
+  if (acc >= threshold) {
+    const unsigned long long pos = atomicAdd(out_count, 1ull);
+    if (pos < static_cast<unsigned long long>(capacity)) {
+      out_pairs[2 * pos] = i;
+      out_pairs[2 * pos + 1] = j;
+    }
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+// Fills h_panel_start (n_my_panels + 1 entries) and returns the launch parameters.
+int64_t sjm_plan(int64_t n_rows, int32_t rank, int32_t world, int64_t* h_panel_start, int32_t max_panels,
+                 int32_t* n_my_panels) {
+  const int64_t nbi = (n_rows + kSjmBM - 1) / kSjmBM, nbj = (n_rows + kSjmBN - 1) / kSjmBN;
+  const int64_t n_panels = (nbj + kSjmPanel - 1) / kSjmPanel;
+  int32_t m = 0;
+  int64_t tiles = 0;
+  for (int64_t pnl = rank; pnl < n_panels && m < max_panels; pnl += world, ++m) {
+    if (h_panel_start) h_panel_start[m] = tiles;
+    int64_t ni = 2 * kSjmPanel * (pnl + 1);
+    if (ni > nbi) ni = nbi;
+    int64_t nj = nbj - pnl * kSjmPanel;
+    if (nj > kSjmPanel) nj = kSjmPanel;
+    tiles += ni * nj;
+  }
+  if (h_panel_start) h_panel_start[m] = tiles;
+  *n_my_panels = m;
+  return tiles;
+}
+
+int64_t sjm_max_panels(int64_t n_rows) {
+  const int64_t nbj = (n_rows + kSjmBN - 1) / kSjmBN;
+  return (nbj + kSjmPanel - 1) / kSjmPanel;
+}
+
+cudaError_t launch_selfjoin_mma(const __nv_bfloat16* emb16, int64_t n_rows, int32_t dim, int64_t ld16,
+                                float thr_lo, int32_t rank, int32_t world, const int64_t* d_panel_start,
+                                int32_t n_my_panels, int64_t total_tiles, int64_t* cand, int64_t cand_cap,
+                                unsigned long long* cand_count, int32_t* flags, int sm_count,
+                                cudaStream_t stream) {
+  if (total_tiles <= 0) return cudaSuccess;
+  if (n_rows > 0x7fffffffll - kSjmBN) return cudaErrorInvalidValue;
+  SjmParams p{};
+  p.n_rows = n_rows;
+  p.k_blocks = (dim + kSjmBK - 1) / kSjmBK;
+  p.thr_lo = thr_lo;
+  p.nbi = (n_rows + kSjmBM - 1) / kSjmBM;
+  p.nbj = (n_rows + kSjmBN - 1) / kSjmBN;
+  p.n_my_panels = n_my_panels;
+  p.panel_begin = rank;
+  p.panel_stride = world;
+  p.panel_start = d_panel_start;
+  p.total_tiles = total_tiles;
+  p.cand = cand; p.cand_cap = cand_cap; p.cand_count = cand_count;
+  CUtensorMap map_a, map_b;
+  if (!make_map(&map_a, emb16, static_cast<uint64_t>(n_rows), static_cast<uint64_t>(dim), static_cast<uint64_t>(ld16), kSjmBM))
+    return cudaErrorNotSupported;
+  if (!make_map(&map_b, emb16, static_cast<uint64_t>(n_rows), static_cast<uint64_t>(dim), static_cast<uint64_t>(ld16), kSjmBN))
+    return cudaErrorNotSupported;
+  const size_t smem = 1024 + static_cast<size_t>(kSjmStages) * kSjmStageBytes + sizeof(SjmShared);
+  cudaError_t e = cudaFuncSetAttribute(selfjoin_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem));
+  if (e != cudaSuccess) return e;
+  int64_t grid = sm_count;
+  if (grid > total_tiles) grid = total_tiles;
+  selfjoin_mma_kernel<<<static_cast<int>(grid), kSjmThreads, smem, stream>>>(map_a, map_b, p, flags);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_selfjoin_recheck(const int64_t* cand, int64_t n_cand, const float* emb, int64_t ld, int32_t dim,
+                                    float threshold, int64_t* out_pairs, int64_t capacity,
+                                    unsigned long long* out_count, cudaStream_t stream) {
+  if (n_cand <= 0) return cudaSuccess;
+  selfjoin_recheck_kernel<<<static_cast<int>((n_cand + 255) / 256), 256, 0, stream>>>(
+      cand, n_cand, emb, ld, dim, threshold, out_pairs, capacity, out_count);
+  return cudaGetLastError();
+}
+
+}  // namespace mmrs

@@ -230,11 +230,16 @@ class ShardedGallery:
         """Self-join with the gallery replicated (10M x 512 fp32 = 20 GB fits every GPU) and the
         upper-triangular tile grid split by equal pair count; variable-length pair lists are
         gathered (counts first, then padded buffers) and sorted lexicographically."""
-        from .dedup import selfjoin_raw, sort_pairs
-        raw_join = raw_join or selfjoin_raw
+        from .dedup import selfjoin_tc_raw, sort_pairs
         n = int(emb_full.shape[0])
-        lo, hi = triangle_bounds(n, self.world)[self.rank]
-        pairs = raw_join(emb_full, threshold, lo, hi) if hi > lo else emb_full.new_empty((0, 2), dtype=torch.int64)
+        if raw_join is None and emb_full.is_cuda and n >= 2048:
+            # tensor-core path: column panels dealt round-robin to the ranks
+            pairs = selfjoin_tc_raw(emb_full, threshold, self.rank, self.world)
+        else:
+            from .dedup import selfjoin_raw
+            raw_join = raw_join or selfjoin_raw
+            lo, hi = triangle_bounds(n, self.world)[self.rank]
+            pairs = raw_join(emb_full, threshold, lo, hi) if hi > lo else emb_full.new_empty((0, 2), dtype=torch.int64)
         if self.world == 1:
             return sort_pairs(pairs, n)
         cnt = torch.tensor([pairs.shape[0]], dtype=torch.int64, device=pairs.device)

@@ -83,3 +83,48 @@ def test_cross_folder_wrapper_matches_reference_golden(mm, tmp_path):
         want = dict(gold["deleted"])[rel(a)]
         assert rel(b) == want or {rel(b), want} == {"reference/sub/c.png", "reference/sub/c_again.png"}
     assert sorted(rel(p) for p in mm.get_all_images(del_dir)) == gold["remaining_in_delete_folder"]
+
+
+# ---- tensor-core prefilter + exact recheck -----------------------------------------------------------
+@pytest.mark.parametrize("n,d,frac", [(2048, 64, 0.05), (5000, 512, 0.02), (20_000, 128, 0.01), (33_333, 768, 0.01),
+                                      (100_000, 64, 0.002)])
+def test_tc_pairs_bit_exact(mm, oracle, n, d, frac):
+    x, planted = oracle.synthetic_dedup(n, d, dup_frac=frac, seed=n)
+    got = mm.find_duplicate_pairs(x, 0.95, method="tc")
+    assert [tuple(p) for p in got.tolist()] == planted
+    if n <= 20_000:
+        assert torch.equal(got, oracle.dedup_pairs(x, 0.95))
+        assert torch.equal(got, mm.find_duplicate_pairs(x, 0.95, method="fp32"))
+
+
+def test_tc_near_threshold_pairs_follow_the_exact_mode(mm, oracle):
+    """No guard band: pairs planted at cosines scattered around tau.  The bf16 pass may let extra
+    candidates through, the fp32 recheck must then take exactly the exact mode's decisions."""
+    gen = torch.Generator().manual_seed(7)
+    n, d = 6000, 256
+    x = oracle.l2_normalize(torch.randn(n, d, generator=gen))
+    for t, c in enumerate(torch.linspace(0.940, 0.960, 400).tolist()):
+        a = x[t]
+        r = torch.randn(d, generator=gen)
+        r = oracle.l2_normalize(r - (r @ a) * a)
+        x[3000 + t] = c * a + (1 - c * c) ** 0.5 * r          # cos(x[t], x[3000 + t]) = c up to rounding
+    want = mm.find_duplicate_pairs(x, 0.95, method="fp32")
+    got = mm.find_duplicate_pairs(x, 0.95, method="tc")
+    assert torch.equal(got, want) and 150 < got.shape[0] < 250
+
+
+def test_tc_rank_panels_partition_the_join(mm, oracle):
+    from mmrs_b200.dedup import selfjoin_tc_raw, sort_pairs, _device_f32
+    x, planted = oracle.synthetic_dedup(40_000, 64, dup_frac=0.01, seed=3)
+    xd = _device_f32(x)
+    parts = [selfjoin_tc_raw(xd, 0.95, r, 3) for r in range(3)]
+    assert sum(p.shape[0] for p in parts) == len(planted)
+    got = sort_pairs(torch.cat(parts), 40_000).cpu()
+    assert [tuple(p) for p in got.tolist()] == planted
+
+
+def test_tc_buffers_regrow(mm, oracle):
+    x = oracle.synthetic_gallery(3000, 64, seed=1, dtype=torch.float32)
+    from mmrs_b200.dedup import selfjoin_tc_raw, sort_pairs, _device_f32
+    got = sort_pairs(selfjoin_tc_raw(_device_f32(x), 0.05, capacity=16), 3000).cpu()   # thousands of pairs
+    assert torch.equal(got, oracle.dedup_pairs(x, 0.05))
