@@ -9,7 +9,8 @@
 //   warp 1 (one lane)  tcgen05.mma issuer: D[tmem] (+)= A[smem] * B[smem], M=128, N=Q, K=16;
 //                      tcgen05.commit frees the smem slot / publishes the accumulator
 //   warp 2             TMEM allocator (2 accumulator stages of Q fp32 columns)
-//   warps 4..7         epilogue: tcgen05.ld the 128xQ accumulator (one gallery row per thread)
+//   warps 4..11        epilogue: tcgen05.ld the 128xQ accumulator (one gallery row per thread,
+//                      two warps per TMEM lane quarter splitting the columns)
 //                      and run the same three epilogues as K1 -- the score matrix never reaches
 //                      HBM unless kModeScores asks for it.
 //
@@ -20,7 +21,8 @@
 
 namespace mmrs {
 
-constexpr int kMmaThreads = 256;
+constexpr int kMmaThreads = 384;         // 4 control warps + 8 epilogue warps
+constexpr int kEpiWarps = 8;             // two per TMEM lane quarter, each takes half of the columns
 constexpr int kBlockM = kTileRows;       // gallery rows per tile == UMMA M
 constexpr int kBlockK = 64;              // bf16 elements per k-block == one 128-byte swizzle row
 constexpr int kUmmaK = 16;
@@ -37,7 +39,7 @@ struct MmaShared {
   uint32_t tmem_base;
   volatile uint32_t abort;
   alignas(16) float thr[kMaxQ];
-  alignas(16) uint2 stash[4][kStash * 32];  // per epilogue thread: parked (column, score) pairs
+  alignas(16) uint2 stash[kEpiWarps][kStash * 32];  // per epilogue thread: parked (column, score) pairs
 };
 
 struct MmaCfg {
@@ -65,7 +67,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < cfg.stages; ++s) { mbar_init(&sh->full[s], 1); mbar_init(&sh->empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&sh->tmem_full[a], 1); mbar_init(&sh->tmem_empty[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&sh->tmem_full[a], 1); mbar_init(&sh->tmem_empty[a], kEpiWarps); }
     sh->abort = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_g)) : "memory");
@@ -145,8 +147,16 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
     }
   } else if (warp >= 4) {
     // ===== epilogue: TMEM -> registers -> keys / scores =====
-    const int ew = warp - 4;                      // == warp % 4: the TMEM lane quarter this warp may read
-    const int r_in_tile = ew * 32 + lane;
+    // warp w may read TMEM lanes 32*(w%4) .. +31.  Warps 4-7 take the first half of the 16-column
+    // chunks, warps 8-11 the second half of the same rows: two epilogue warps per scheduler hide
+    // each other's TMEM-load and shared-memory latencies (with one the 256-query kernel was
+    // epilogue-bound: tensor pipe 45 % active, profiles/r01_k2_b256_source.txt).
+    const int ew = warp - 4;
+    const int quarter = ew & 3, half = ew >> 2;
+    const int r_in_tile = quarter * 32 + lane;
+    const int n_chunks = cfg.n_umma / 16;
+    const int c_begin = half == 0 ? 0 : ((n_chunks + 1) / 2) * 16;
+    const int c_end = half == 0 ? ((n_chunks + 1) / 2) * 16 : cfg.n_umma;
     const int64_t last_row = p.n_rows - 1;
     uint32_t it = 0;
     bool ok = true;
@@ -158,7 +168,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
       tcgen05_fence_after();
       const int64_t row = static_cast<int64_t>(t) * kBlockM + r_in_tile;
       const bool row_ok = row <= last_row;
-      const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) +
+      const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                               as * static_cast<uint32_t>(cfg.acc_stride);
       if constexpr (MODE == kModeFilter) {
         // One sweep over the accumulator; a passing (column, score) is parked in this thread's
@@ -187,13 +197,9 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
           }
           n_st = 0;
         };
-        for (int c0 = 0; c0 < cfg.n_umma; c0 += 16) {
-          uint32_t acc[16];
-          __syncwarp();
-          tmem_ld16(taddr0 + static_cast<uint32_t>(c0), acc);
-          tmem_ld_wait();
-          // branch-free pass mask for the 16 columns (one warp per scheduler runs this loop, so
-          // every taken branch would expose its full latency), then a short loop over set bits
+        auto process16 = [&](const uint32_t (&acc)[16], int c0) {
+          // branch-free pass mask for the 16 columns (every taken branch would expose its full
+          // latency), then a short loop over the set bits
           const float4* thr4 = reinterpret_cast<const float4*>(sh->thr + c0);
           uint32_t bits = 0;
 #pragma unroll
@@ -217,10 +223,20 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
             my_stash[n_st * 32] = make_uint2(static_cast<uint32_t>(c0 + c), __float_as_uint(__uint_as_float(a) * p.scale));
             ++n_st;
           }
+        };
+        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+          uint32_t acc0[16], acc1[16];
+          const bool two = c0 + 16 < c_end;     // warp-uniform
+          __syncwarp();
+          tmem_ld16(taddr0 + static_cast<uint32_t>(c0), acc0);
+          if (two) tmem_ld16(taddr0 + static_cast<uint32_t>(c0 + 16), acc1);   // both loads in flight
+          tmem_ld_wait();
+          process16(acc0, c0);
+          if (two) process16(acc1, c0 + 16);
         }
         if (n_st) flush();
       } else {
-      for (int c0 = 0; c0 < cfg.n_umma; c0 += 16) {
+      for (int c0 = c_begin; c0 < c_end; c0 += 16) {
         uint32_t acc[16];
         __syncwarp();
         tmem_ld16(taddr0 + static_cast<uint32_t>(c0), acc);
