@@ -136,8 +136,9 @@ constexpr int kSuperChunk = 1024;  // queries sharing one set of candidate lists
 // search scale with n_queries * k * ratio * (#phases - 1): small batches take few, coarse phases
 // (launch-bound), large batches finer ones (append-bound).  Measured on B200: tools/tune_plan.sh.
 static SearchPlan plan_for(int64_t n_rows, int32_t k, int32_t n_queries) {
-  const int ratio_dflt = n_queries <= 128 ? 4 : 3;
-  const int dense_dflt = n_queries <= 32 ? 16 : (n_queries <= 64 ? 32 : 64);
+  // profiles/r01_tune4.log: seed sample of 32-64 tiles, a mid phase 8x as large, everything else last
+  const int ratio_dflt = 3;
+  const int dense_dflt = n_queries <= 48 ? 32 : 64;
   return make_search_plan(n_rows, k, kTileRows, env_int("MMRS_RATIO_LOG2", ratio_dflt),
                           env_int("MMRS_DENSE_TILES", dense_dflt));
 }

@@ -32,7 +32,7 @@ extern "C" int plan(long long n, int k, int ratio, int dense, int* out) {{
     return ctypes.CDLL(str(so))
 
 
-def get_plan(lib, n, k, ratio=5, dense=16):
+def get_plan(lib, n, k, ratio=3, dense=32):
     out = (ctypes.c_int * 64)()
     lib.plan(ctypes.c_longlong(n), k, ratio, dense, out)
     phases = [(out[4 + 3 * i], out[5 + 3 * i], out[6 + 3 * i]) for i in range(out[1])]
