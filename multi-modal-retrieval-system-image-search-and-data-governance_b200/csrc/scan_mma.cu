@@ -17,6 +17,8 @@
 // The accumulator is double buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
 // Roofline: HBM-bound (N*D*2 bytes per pass) up to Q ~ 200, tensor-bound beyond
 // (SURVEY.md section 8d).
+#include <stdlib.h>
+
 #include "tcgen05_utils.cuh"
 
 namespace mmrs {
@@ -52,7 +54,7 @@ struct MmaCfg {
 
 
 template <int MODE>
-__global__ void __launch_bounds__(kMmaThreads, 1)
+__global__ void __launch_bounds__(kMmaThreads, 2)
 scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_q,
                 const ScanParams p, const MmaCfg cfg, int32_t* flags) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -295,7 +297,12 @@ cudaError_t launch_scan_mma(const ScanParams& p, const __nv_bfloat16* q_bf16, in
   cfg.tmem_cols = cols;
   cfg.acc_stride = cols / 2;
   const size_t stage_bytes = static_cast<size_t>(kABytes) + static_cast<size_t>(cfg.n_umma) * kBlockK * 2;
-  const size_t budget = 227 * 1024 - sizeof(MmaShared) - 1024;   // alignment slack
+  // Up to 64 queries the CTA is sized so that TWO fit on an SM (<= 113 KB of shared memory, 80
+  // registers x 384 threads, <= 128 TMEM columns each): the scans of two searches in flight on
+  // different streams then share the HBM stream instead of queueing behind each other, and the
+  // short seed/mid scans of one search hide under the long last-phase scan of the other.
+  const bool small = cfg.n_umma <= 64 && getenv("MMRS_K2_BIG_SMEM") == nullptr;
+  const size_t budget = (small ? 113 * 1024 : 227 * 1024) - sizeof(MmaShared) - 1024 - (small ? 1024 : 0);
   int stages = static_cast<int>(budget / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return cudaErrorInvalidValue;
@@ -310,7 +317,11 @@ cudaError_t launch_scan_mma(const ScanParams& p, const __nv_bfloat16* q_bf16, in
                 static_cast<uint64_t>(p.ldq), static_cast<uint32_t>(cfg.n_umma)))
     return cudaErrorNotSupported;
 
-  int grid = sm_count;
+  // 33..64 queries: the small-footprint CTA has only 4 ring stages, so one launch fills both CTA
+  // slots of every SM itself (measured: 0.202 vs 0.224 ms per step at 64 queries)
+  int ctas_per_sm = (small && cfg.n_umma > 32) ? 2 : 1;
+  if (const char* e = getenv("MMRS_K2_CTAS_PER_SM")) ctas_per_sm = atoi(e) == 2 && small ? 2 : 1;
+  int grid = sm_count * ctas_per_sm;
   if (grid > p.sched.n_sel) grid = p.sched.n_sel;
   if (grid < 1) grid = 1;
   auto go = [&](auto kernel) -> cudaError_t {

@@ -83,10 +83,11 @@ class DeviceGallery:
             self._workspaces[key] = buf
         return buf
 
-    def search_workspace(self, nq: int, k: int, host_io: bool):
+    def search_workspace(self, nq: int, k: int, host_io: bool, stream_id: int = 0):
         """(aligned device pointer, byte size) of the scratch space of one search shape; sized by
-        the library's own query and cached, so a steady-state call allocates nothing."""
-        key = ("search", nq, k, host_io)
+        the library's own query and cached, so a steady-state call allocates nothing.  One per
+        stream: searches in flight on different streams must not share candidate lists."""
+        key = ("search", nq, k, host_io, stream_id)
         hit = self._workspaces.get(key)
         if hit is None:
             lib = _cabi.lib

@@ -108,7 +108,8 @@ def search_topk(queries, gallery: GalleryLike, k: int, *, normalize_queries: boo
     dev = gal.device
     if torch.cuda.current_device() != dev.index:
         torch.cuda.set_device(dev)
-    ws_ptr, ws_bytes = gal.search_workspace(nq, k, on_host)
+    stream = torch.cuda.current_stream(dev)
+    ws_ptr, ws_bytes = gal.search_workspace(nq, k, on_host, stream.cuda_stream)
     if on_host:
         if nq > 0 and not q.is_pinned():
             q = q.pin_memory()
@@ -122,7 +123,6 @@ def search_topk(queries, gallery: GalleryLike, k: int, *, normalize_queries: boo
     args = (gal.data.data_ptr(), gal.n_rows, gal.padded_dim, gal.data.stride(0), gal.dtype_code,
             q.data_ptr(), nq, q.stride(0), k, int(bool(normalize_queries)), float(scale),
             gal.row_offset, _cabi.PATHS[path], values.data_ptr(), indices.data_ptr(), ws_ptr, ws_bytes)
-    stream = torch.cuda.current_stream(dev)
     if sync:
         fn = lib.mmrs_search_topk_host if on_host else lib.mmrs_search_topk
         _cabi.check(fn(*args, stream.cuda_stream))

@@ -138,7 +138,7 @@ class ShardedGallery:
         buf = torch.zeros(n_keys + 1, dtype=torch.int64, device=dev)      # key 0 = "no entry"; [-1] = status
         status = torch.zeros(2, dtype=torch.int32).pin_memory()
         stream = torch.cuda.current_stream(dev)
-        ws_ptr, ws_bytes = gal.search_workspace(nq, k_local, False)
+        ws_ptr, ws_bytes = gal.search_workspace(nq, k_local, False, stream.cuda_stream)
         if nq:
             dst = buf if k_local == k else torch.empty(nq * k_local + 1, dtype=torch.int64, device=dev)
             _cabi.check(lib.mmrs_search_topk_keys_async(
