@@ -278,7 +278,9 @@ def main():
     ms_total = ev0.elapsed_time(ev1)
     launches = lib.mmrs_launch_count() - launches0
     # synchronous per-call latency of the same search (one batch in flight, host blocks on each)
-    torch.cuda.synchronize()
+    for _ in range(3):
+        search_dev()                    # one-time set-up of the default-stream slot stays untimed
+    barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         search_dev()
@@ -348,6 +350,9 @@ def main():
     tt = torch.tensor([dt], device=device)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    for _ in range(3):
+        search_host()
+    barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         search_host()

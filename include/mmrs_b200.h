@@ -179,6 +179,30 @@ int mmrs_topk_merge_keys_async(const uint64_t* d_keys_in, int32_t n_lists, int32
                                float* d_out_values, int64_t* d_out_indices, int32_t* d_status,
                                int32_t* h_status, void* stream);
 
+/*
+ * Search fused with its all-gather (one process per GPU, NVLink peer memory instead of NCCL):
+ * every rank's LAST select stores its top-k_local keys directly into every rank's gather buffer
+ * (d_peer_bufs[r] = rank r's buffer, peer-mapped, world * list_stride uint64; rank s owns the
+ * slice [s * list_stride, +n_queries * k_local] plus one status word), the last CTA publishes a
+ * "ready" flag to every rank with release semantics, and the merge select on each rank starts as
+ * soon as all `world` flags carry this call's epoch -- no collective launch, no host round trip.
+ * d_peer_flags[r] = rank r's flag array (2 * world uint32, zero-initialised once): [0, world) ready,
+ * [world, 2*world) ack (a rank acks after merging; producers wait for the acks of epoch - 1 before
+ * overwriting a buffer).  `epoch` = 1, 2, 3, ... per (buffer, flag array) pair, identical on all
+ * ranks; calls are collective: same order on every rank.  d_local_buf = this rank's own buffer.
+ * h_status: pinned int32 [2 * world + 2]; after the stream has completed,
+ * mmrs_gather_status(h_status, world) is the outcome on every rank alike (MMRS_ERR_RETRY when any
+ * rank overflowed).  n_queries <= 1024.
+ */
+int mmrs_search_topk_fused_gather_async(
+    const void* d_gallery, int64_t n_rows, int32_t dim, int64_t ld_gallery, int32_t gallery_dtype,
+    const float* d_queries, int32_t n_queries, int64_t ld_queries, int32_t k_local, int32_t k_out,
+    int32_t normalize_queries, float scale, int64_t index_offset, int32_t path,
+    uint64_t* const* d_peer_bufs, uint32_t* const* d_peer_flags, uint64_t* d_local_buf, int32_t rank,
+    int32_t world, int64_t list_stride, uint32_t epoch, float* d_out_values, int64_t* d_out_indices,
+    void* d_workspace, size_t workspace_bytes, int32_t* h_status, void* stream);
+int mmrs_gather_status(const int32_t* h_status, int32_t world);
+
 /* ---- multi-GPU merge -------------------------------------------------------------------- */
 
 size_t mmrs_topk_merge_workspace_bytes(int32_t n_lists, int32_t n_queries, int32_t k_in);

@@ -56,6 +56,10 @@ SIGNATURES = {
     "mmrs_search_topk_host_async": (C.c_int, [_vp, _i64, _i32, _i64, _i32, _vp, _i32, _i64, _i32, _i32,
                                               _f32, _i64, _i32, _vp, _vp, _vp, _sz, _vp, _vp]),
     "mmrs_search_status": (C.c_int, [_vp]),
+    "mmrs_search_topk_fused_gather_async": (C.c_int, [_vp, _i64, _i32, _i64, _i32, _vp, _i32, _i64, _i32, _i32, _i32,
+                                                      _f32, _i64, _i32, _vp, _vp, _vp, _i32, _i32, _i64, C.c_uint32,
+                                                      _vp, _vp, _vp, _sz, _vp, _vp]),
+    "mmrs_gather_status": (C.c_int, [_vp, _i32]),
     "mmrs_search_topk_keys_async": (C.c_int, [_vp, _i64, _i32, _i64, _i32, _vp, _i32, _i64, _i32, _i32, _f32,
                                               _i64, _i32, _vp, _vp, _sz, _vp, _vp]),
     "mmrs_topk_merge_keys_async": (C.c_int, [_vp, _i32, _i32, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),

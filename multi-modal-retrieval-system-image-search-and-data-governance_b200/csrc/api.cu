@@ -154,6 +154,7 @@ struct Workspace {
   uint32_t* cnt;           // [Qs]
   uint64_t* cand;          // [Qs, cap] (>= n_tiles * kTileRows keys for the exhaustive path)
   size_t cand_keys;
+  uint32_t* gscratch;      // [8]: [0] epoch, [1] producer CTA counter, [2] consumer CTA counter, [4] merge status
   size_t total;
 };
 
@@ -165,6 +166,7 @@ static Workspace carve(void* base, int64_t n_rows, int32_t dim, int32_t n_querie
   auto take = [&](size_t bytes) { char* p = b ? b + off : nullptr; off += align_up(bytes, 256); return p; };
   const int32_t ldq = padded_dim(dim), qp = padded_queries(n_queries);
   w.flags = reinterpret_cast<int32_t*>(take(8 * sizeof(int32_t)));
+  w.gscratch = reinterpret_cast<uint32_t*>(take(8 * sizeof(uint32_t)));
   w.q_f32 = reinterpret_cast<float*>(take(static_cast<size_t>(qp) * ldq * sizeof(float)));
   w.q_bf16 = reinterpret_cast<__nv_bfloat16*>(take(static_cast<size_t>(qp) * ldq * sizeof(__nv_bfloat16)));
   if (with_lists) {
@@ -291,6 +293,11 @@ struct SearchArgs {
   int32_t k; int32_t normalize; float scale; int64_t index_offset; int32_t path;
   float* d_values; int64_t* d_indices;
   uint64_t* d_keys = nullptr;   // optional: packed (score, ~global row) keys instead of / besides the pair
+  // fused all-gather (producer side of the last select)
+  int32_t g_world = 0, g_rank = 0;
+  uint64_t* const* g_peer_bufs = nullptr;
+  uint32_t* const* g_peer_flags = nullptr;
+  int64_t g_list_stride = 0;
 };
 
 // Enqueue the whole fused search on `stream`.  Results are valid iff the flag word stays 0.
@@ -338,6 +345,12 @@ static int enqueue_search(const SearchArgs& a, const DeviceInfo& dev, const Work
       sp.out_keys = a.d_keys ? a.d_keys + static_cast<int64_t>(s0) * a.k : nullptr;
       sp.index_offset = a.index_offset;
       sp.flags = w.flags;
+      if (a.g_world > 0 && sp.final_pass) {
+        sp.g_role = 1; sp.g_world = a.g_world; sp.g_rank = a.g_rank;
+        sp.g_peer_bufs = a.g_peer_bufs; sp.g_peer_flags = a.g_peer_flags;
+        sp.g_list_stride = a.g_list_stride; sp.g_status_index = a.n_queries * a.k;
+        sp.g_epoch = w.gscratch; sp.g_counter = w.gscratch + 1;
+      }
       rc = profiled_launch(3, 0, 0, stream, [&]() { return launch_select(sp, ns, stream); });
       if (rc != MMRS_OK) return rc;
     }
@@ -385,8 +398,10 @@ struct GraphKey {
   const float* d_queries; int32_t n_queries; int64_t ldq_in; int32_t k; int32_t normalize;
   float scale; int64_t index_offset; int32_t path; float* d_values; int64_t* d_indices;
   void* workspace; int device; int ratio_log2; int dense_tiles; uint64_t* d_keys;
+  int32_t g_world, g_rank; const void* g_bufs; const void* g_flags; int64_t g_stride;
   bool operator==(const GraphKey& o) const {
-    return d_keys == o.d_keys && gallery == o.gallery && n_rows == o.n_rows && dim == o.dim && ld == o.ld && dtype == o.dtype &&
+    return g_world == o.g_world && g_rank == o.g_rank && g_bufs == o.g_bufs && g_flags == o.g_flags &&
+           g_stride == o.g_stride && d_keys == o.d_keys && gallery == o.gallery && n_rows == o.n_rows && dim == o.dim && ld == o.ld && dtype == o.dtype &&
            d_queries == o.d_queries && n_queries == o.n_queries && ldq_in == o.ldq_in && k == o.k &&
            normalize == o.normalize && scale == o.scale && index_offset == o.index_offset &&
            path == o.path && d_values == o.d_values && d_indices == o.d_indices &&
@@ -406,7 +421,8 @@ static int launch_search_graph(const SearchArgs& a, const DeviceInfo& dev, const
     return enqueue_search(a, dev, w, stream);   // event-bracketed launches are issued directly
   GraphKey key{a.gallery, a.n_rows, a.dim, a.ld, a.dtype, a.d_queries, a.n_queries, a.ldq_in, a.k,
                a.normalize, a.scale, a.index_offset, a.path, a.d_values, a.d_indices, workspace,
-               dev.device, env_int("MMRS_RATIO_LOG2", -1), env_int("MMRS_DENSE_TILES", -1), a.d_keys};
+               dev.device, env_int("MMRS_RATIO_LOG2", -1), env_int("MMRS_DENSE_TILES", -1), a.d_keys,
+               a.g_world, a.g_rank, a.g_peer_bufs, a.g_peer_flags, a.g_list_stride};
   cudaGraphExec_t exec = nullptr;
   long long kernels = 0;
   {
@@ -573,7 +589,7 @@ static int search_enqueue(SearchArgs& a, const float* h_queries, float* h_values
   if (!h_status) return fail(MMRS_ERR_ARG, "null status pointer");
   h_status[0] = 0;
   if (a.n_queries == 0) return MMRS_OK;
-  if (!host_io && (!a.d_queries || (!a.d_keys && (!a.d_values || !a.d_indices))))
+  if (!host_io && (!a.d_queries || (!a.d_keys && a.g_world == 0 && (!a.d_values || !a.d_indices))))
     return fail(MMRS_ERR_ARG, "null query / output pointer");
   const Workspace w = carve(d_workspace, a.n_rows, a.dim, a.n_queries, a.k, true);
   const size_t vbytes = static_cast<size_t>(a.n_queries) * a.k * sizeof(float);
@@ -739,6 +755,74 @@ int mmrs_topk_merge_keys_async(const uint64_t* d_keys_in, int32_t n_lists, int32
   MMRS_LAUNCH(launch_select(sp, n_queries, stream));
   MMRS_CUDA(cudaMemcpyAsync(h_status, d_status, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
   return MMRS_OK;
+}
+
+int mmrs_search_topk_fused_gather_async(const void* d_gallery, int64_t n_rows, int32_t dim, int64_t ld_gallery,
+                                        int32_t gallery_dtype, const float* d_queries, int32_t n_queries,
+                                        int64_t ld_queries, int32_t k_local, int32_t k_out,
+                                        int32_t normalize_queries, float scale, int64_t index_offset, int32_t path,
+                                        uint64_t* const* d_peer_bufs, uint32_t* const* d_peer_flags,
+                                        uint64_t* d_local_buf, int32_t rank, int32_t world, int64_t list_stride,
+                                        uint32_t epoch, float* d_out_values, int64_t* d_out_indices,
+                                        void* d_workspace, size_t workspace_bytes, int32_t* h_status, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (world < 1 || world > 64 || rank < 0 || rank >= world || !d_peer_bufs || !d_peer_flags || !d_local_buf)
+    return fail(MMRS_ERR_ARG, "bad rank / world / peer pointers");
+  if (n_queries < 1 || n_queries > kSuperChunk)
+    return fail(MMRS_ERR_ARG, "fused gather handles 1..%d queries per call", kSuperChunk);
+  if (k_local < 1 || k_out < 1 || k_out > 1024 || static_cast<int64_t>(world) * k_local < k_out)
+    return fail(MMRS_ERR_ARG, "bad k_local / k_out");
+  if (list_stride < static_cast<int64_t>(n_queries) * k_local + 1)
+    return fail(MMRS_ERR_ARG, "list_stride must be at least n_queries * k_local + 1");
+  if (index_offset < 0 || index_offset + n_rows > 0x100000000ll)
+    return fail(MMRS_ERR_ARG, "global row ids must fit 32 bits");
+  if (epoch == 0) return fail(MMRS_ERR_ARG, "epochs start at 1");
+  if (!d_out_values || !d_out_indices || !h_status) return fail(MMRS_ERR_ARG, "null output pointer");
+  SearchArgs a{d_gallery, n_rows, dim, ld_gallery, gallery_dtype, d_queries, n_queries, ld_queries,
+               k_local, normalize_queries, scale, index_offset, path, nullptr, nullptr};
+  a.g_world = world; a.g_rank = rank; a.g_peer_bufs = d_peer_bufs; a.g_peer_flags = d_peer_flags;
+  a.g_list_stride = list_stride;
+  // the epoch has to be on the device before the graph's producer select reads it
+  {
+    DeviceInfo dev0;
+    int rc0 = current_device(&dev0);
+    if (rc0 != MMRS_OK) return rc0;
+    const size_t need = mmrs_search_workspace_bytes(n_rows, dim, gallery_dtype, n_queries, k_local);
+    if (!d_workspace || workspace_bytes < need) return fail(MMRS_ERR_WORKSPACE, "workspace %zu bytes, need %zu", workspace_bytes, need);
+  }
+  const Workspace w0 = carve(d_workspace, n_rows, dim, n_queries, k_local, true);
+  MMRS_CUDA(cudaMemsetAsync(w0.gscratch, 0, 8 * sizeof(uint32_t), stream));   // counters, merge status
+  MMRS_LAUNCH(launch_fill_u32(w0.gscratch, epoch, 1, stream));
+  Workspace w{};
+  int rc = search_enqueue(a, nullptr, nullptr, nullptr, d_workspace, workspace_bytes, h_status + world + 1, stream,
+                          nullptr, &w);
+  if (rc != MMRS_OK) return rc;
+  // consumer: merge the lists every rank stored into MY gather buffer, as soon as all have arrived
+  SelectParams sp{};
+  sp.cand = d_local_buf;
+  sp.cap = world * k_local; sp.fixed_n = world * k_local; sp.k = k_out; sp.final_pass = 1;
+  sp.out_values = d_out_values; sp.out_indices = d_out_indices; sp.index_offset = 0;
+  sp.flags = reinterpret_cast<int32_t*>(w.gscratch + 4);
+  sp.seg_len = k_local; sp.seg_stride = list_stride;
+  sp.g_role = 2; sp.g_world = world; sp.g_rank = rank; sp.g_peer_bufs = d_peer_bufs; sp.g_peer_flags = d_peer_flags;
+  sp.g_list_stride = list_stride; sp.g_status_index = n_queries * k_local;
+  sp.g_epoch = w.gscratch; sp.g_counter = w.gscratch + 2;
+  MMRS_LAUNCH(launch_select(sp, n_queries, stream));
+  // every rank's status word (gathered with its keys) and the merge's own flags
+  MMRS_CUDA(cudaMemcpy2DAsync(h_status, sizeof(int32_t), d_local_buf + static_cast<int64_t>(n_queries) * k_local,
+                              static_cast<size_t>(list_stride) * sizeof(uint64_t), sizeof(int32_t), world,
+                              cudaMemcpyDeviceToHost, stream));
+  MMRS_CUDA(cudaMemcpyAsync(h_status + world, w.gscratch + 4, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  return MMRS_OK;
+}
+
+int mmrs_gather_status(const int32_t* h_status, int32_t world) {
+  if (!h_status || world < 1) return fail(MMRS_ERR_ARG, "bad arguments");
+  int32_t all = 0;
+  for (int r = 0; r <= world; ++r) all |= h_status[r];
+  if (all == kFlagOverflow)
+    return fail(MMRS_ERR_RETRY, "a candidate list overflowed on some rank: every rank repeats the batch on the general path");
+  return flags_to_status(all);
 }
 
 int mmrs_search_status(const int32_t* h_status) {

@@ -136,6 +136,15 @@ struct SelectParams {
   // element i of query q's list lives at cand[(i / seg_len) * seg_stride + q * seg_len + i % seg_len]
   int32_t seg_len;        // 0 = plain [n_queries, cap] layout
   int64_t seg_stride;
+  // fused all-gather over NVLink peer memory (multi-GPU, see api.cu: mmrs_search_topk_fused_gather_async)
+  int32_t g_role;                  // 0 none, 1 producer (last select of the local search), 2 consumer (merge)
+  int32_t g_world, g_rank;
+  uint64_t* const* g_peer_bufs;    // [g_world] every rank's gather buffer (peer-mapped)
+  uint32_t* const* g_peer_flags;   // [g_world] every rank's flag array: [0,world) ready, [world,2*world) ack
+  int64_t g_list_stride;           // elements between two ranks' lists inside a gather buffer
+  int32_t g_status_index;          // element of a list that carries the rank's status word
+  const uint32_t* g_epoch;         // device: sequence number of this call on this slot (starts at 1)
+  uint32_t* g_counter;             // device: CTAs done (returns to 0)
 };
 
 // launchers (defined in the .cu files, called from api.cu)

@@ -248,9 +248,13 @@ __device__ __forceinline__ void select_body(const SelectParams& p, SelShared& sh
       const int64_t grow = static_cast<int64_t>(key_row(mine)) + p.index_offset;
       if (p.out_values) p.out_values[static_cast<int64_t>(q) * k + rank] = key_score(mine);
       if (p.out_indices) p.out_indices[static_cast<int64_t>(q) * k + rank] = grow;
-      if (p.out_keys)
-        p.out_keys[static_cast<int64_t>(q) * k + rank] =
-            (mine & 0xffffffff00000000ull) | static_cast<uint64_t>(~static_cast<uint32_t>(grow));
+      const uint64_t gkey = (mine & 0xffffffff00000000ull) | static_cast<uint64_t>(~static_cast<uint32_t>(grow));
+      if (p.out_keys) p.out_keys[static_cast<int64_t>(q) * k + rank] = gkey;
+      if (p.g_role == 1) {
+        // fused all-gather: store the key straight into every rank's gather buffer over NVLink
+        const int64_t off = static_cast<int64_t>(p.g_rank) * p.g_list_stride + static_cast<int64_t>(q) * k + rank;
+        for (int r = 0; r < p.g_world; ++r) p.g_peer_bufs[r][off] = gkey;
+      }
     }
   } else {
     // next list = the winners (unsorted); bound = score part of the pivot (<= every winner's score)
@@ -258,6 +262,30 @@ __device__ __forceinline__ void select_body(const SelectParams& p, SelShared& sh
     if (tid == 0) {
       p.cnt[q] = n_win;
       p.thr[q] = key_score(thr_key);
+    }
+  }
+}
+
+__device__ void select_dispatch(const SelectParams& p, SelShared& sh, uint64_t* list, int q);
+
+// ---- flags exchanged between GPUs (system scope) ----------------------------------------------------
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Wait until flags[i] >= want for every i in [0, n).  Bounded: a peer that never arrives must end
+// this kernel with a status flag, not hang the GPU (the waiters run on OTHER GPUs than the
+// producers they wait for, so this is not two kernels spinning on each other on one device).
+__device__ __forceinline__ void wait_all_ge(const uint32_t* flags, int n, uint32_t want, int32_t* status) {
+  for (int i = 0; i < n; ++i) {
+    uint32_t spins = 0;
+    while (static_cast<int32_t>(ld_acquire_sys(flags + i) - want) < 0) {
+      if (++spins > (1u << 22)) { atomicOr(status, kFlagWatchdog); return; }
+      __nanosleep(64);
     }
   }
 }
@@ -270,6 +298,43 @@ __global__ void __launch_bounds__(kSelThreads, 1) select_topk_kernel(const Selec
   pdl_launch_dependents();
   pdl_wait();   // the list and its length come from the preceding scan
 
+  if (p.g_role != 0) {
+    // producer: every rank must have finished MERGING the previous use of this slot before its
+    //           buffer is overwritten (ack >= epoch - 1); consumer: every rank's keys of this epoch
+    //           must have landed here (ready >= epoch).
+    if (tid == 0) {
+      const uint32_t epoch = *p.g_epoch;
+      const uint32_t* mine = p.g_peer_flags[p.g_rank];
+      if (p.g_role == 1) wait_all_ge(mine + p.g_world, p.g_world, epoch - 1, p.flags);
+      else wait_all_ge(mine, p.g_world, epoch, p.flags);
+    }
+    __syncthreads();
+  }
+  select_dispatch(p, sh, list, q);
+  if (p.g_role != 0) {
+    // last CTA out publishes: status word + "ready" (producer) or "ack" (consumer) to every rank
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+      const uint32_t done = atomicAdd(p.g_counter, 1u);
+      if (done == gridDim.x - 1) {
+        *p.g_counter = 0;
+        const uint32_t epoch = *p.g_epoch;
+        if (p.g_role == 1) {
+          const uint64_t status = static_cast<uint64_t>(static_cast<uint32_t>(*reinterpret_cast<volatile int32_t*>(p.flags)));
+          for (int r = 0; r < p.g_world; ++r)
+            p.g_peer_bufs[r][static_cast<int64_t>(p.g_rank) * p.g_list_stride + p.g_status_index] = status;
+          __threadfence_system();
+        }
+        const int slot = (p.g_role == 1 ? 0 : p.g_world) + p.g_rank;
+        for (int r = 0; r < p.g_world; ++r) st_release_sys(p.g_peer_flags[r] + slot, epoch);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void select_dispatch_impl(const SelectParams& p, SelShared& sh, uint64_t* list, int q) {
+  const int tid = threadIdx.x;
   uint32_t n;
   if (p.fixed_n >= 0) {
     n = static_cast<uint32_t>(p.fixed_n);
@@ -294,6 +359,9 @@ __global__ void __launch_bounds__(kSelThreads, 1) select_topk_kernel(const Selec
   else if (kpt <= 8) select_body<8>(p, sh, list, n, q);
   else if (kpt <= kSelMaxKpt) select_body<16>(p, sh, list, n, q);
   else select_body<0>(p, sh, list, n, q);
+}
+__device__ void select_dispatch(const SelectParams& p, SelShared& sh, uint64_t* list, int q) {
+  select_dispatch_impl(p, sh, list, q);
 }
 
 cudaError_t launch_select(const SelectParams& p, int32_t n_queries, cudaStream_t stream) {

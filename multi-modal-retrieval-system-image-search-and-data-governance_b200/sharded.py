@@ -104,6 +104,9 @@ class ShardedGallery:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self._fast = local_search is None and merge is None   # product path: packed-key pipeline
+        self._fused = {}
+        import os
+        self._fused_ok = os.environ.get("MMRS_NO_FUSED_GATHER", "0") != "1"
         if local_search is None:
             from .search import search_topk as local_search
         self._search = local_search
@@ -185,6 +188,77 @@ class ShardedGallery:
         finish._keepalive = (q, buf, gathered)
         return finish
 
+    # ---- search fused with its all-gather over NVLink peer memory -----------------------------------
+    def _fused_state(self, nq: int, k_local: int, stream_id: int):
+        """Symmetric (peer-mapped) gather buffer + flag array of one (shape, stream) slot; the
+        rendezvous is collective and happens once per slot."""
+        key = (nq, k_local, stream_id)
+        st = self._fused.get(key)
+        if st is None:
+            import torch.distributed._symmetric_memory as symm_mem
+            dev = self.local.device
+            stride = nq * k_local + 1                       # one list + the rank's status word
+            total = self.world * stride + self.world         # + 2 * world uint32 flags
+            t = symm_mem.empty(total, dtype=torch.int64, device=dev)
+            t.zero_()
+            hdl = symm_mem.rendezvous(t, self.group if self.group is not None else dist.group.WORLD)
+            torch.cuda.synchronize(dev)
+            dist.barrier(group=self.group)                   # everyone zeroed before anyone stores
+            ptrs = [int(x) for x in hdl.buffer_ptrs]
+            st = {"t": t, "hdl": hdl, "stride": stride, "epoch": 0,
+                  "bufs": torch.tensor(ptrs, dtype=torch.int64, device=dev),
+                  "flags": torch.tensor([x + self.world * stride * 8 for x in ptrs], dtype=torch.int64, device=dev)}
+            self._fused[key] = st
+        return st
+
+    def _search_topk_fused(self, queries, k: int, normalize_queries: bool, scale: float, path: str):
+        """Local scan -> last select stores its keys into EVERY rank's buffer over NVLink and raises
+        a ready flag -> merge select waits for all flags.  One library call, no NCCL, no host sync
+        until the final status check."""
+        from .search import _prep_queries
+        gal = self.local
+        q, on_host = _prep_queries(queries, gal)
+        if on_host:
+            q = q.to(gal.device, non_blocking=True)
+        nq = int(q.shape[0])
+        dev = gal.device
+        lib = _cabi.lib
+        if torch.cuda.current_device() != dev.index:
+            torch.cuda.set_device(dev)
+        k_local = min(k, gal.n_rows)
+        stream = torch.cuda.current_stream(dev)
+        st = self._fused_state(nq, k_local, stream.cuda_stream)
+        st["epoch"] += 1
+        ws_ptr, ws_bytes = gal.search_workspace(nq, k_local, False, stream.cuda_stream)
+        out_v = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        out_i = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        status = torch.zeros(2 * self.world + 2, dtype=torch.int32).pin_memory()
+        _cabi.check(lib.mmrs_search_topk_fused_gather_async(
+            gal.data.data_ptr(), gal.n_rows, gal.padded_dim, gal.data.stride(0), gal.dtype_code,
+            q.data_ptr(), nq, q.stride(0), k_local, k, int(bool(normalize_queries)), float(scale),
+            gal.row_offset, _cabi.PATHS[path], st["bufs"].data_ptr(), st["flags"].data_ptr(),
+            st["t"].data_ptr(), self.rank, self.world, st["stride"], st["epoch"],
+            out_v.data_ptr(), out_i.data_ptr(), ws_ptr, ws_bytes, status.data_ptr(), stream.cuda_stream))
+        if on_host:
+            hv = torch.empty((nq, k), dtype=torch.float32, pin_memory=True)
+            hi = torch.empty((nq, k), dtype=torch.int64, pin_memory=True)
+            hv.copy_(out_v, non_blocking=True)
+            hi.copy_(out_i, non_blocking=True)
+            out_v, out_i = hv, hi
+        event = torch.cuda.Event()
+        event.record(stream)
+
+        def finish():
+            event.synchronize()
+            rc = lib.mmrs_gather_status(status.data_ptr(), self.world)
+            if rc == _cabi.ERR_RETRY:
+                return None                  # the same verdict on every rank: all take the general path
+            _cabi.check(rc)
+            return out_v, out_i
+
+        finish._keepalive = (q, status)
+        return finish
+
     def search_topk(self, queries: torch.Tensor, k: int, *, normalize_queries: bool = True,
                     scale: float = 1.0, path: str = "auto", sync: bool = True):
         """Global top-k, identical on every rank.  `queries` must be the same on all ranks.
@@ -193,7 +267,17 @@ class ShardedGallery:
         if k > self.n_rows_global:
             raise RuntimeError("selected index k out of range")
         if self._fast and self.world > 1:
-            finish = self._search_topk_keys(queries, k, normalize_queries, scale, path)
+            nq = int(queries.shape[0]) if hasattr(queries, "shape") and len(queries.shape) == 2 else 1
+            fused = self._fused_ok and 1 <= nq <= 1024
+            if fused:
+                try:
+                    finish = self._search_topk_fused(queries, k, normalize_queries, scale, path)
+                except (ImportError, AttributeError, RuntimeError) as e:   # no symmetric memory here
+                    if isinstance(e, _cabi.MmrsError):
+                        raise
+                    self._fused_ok = fused = False
+            if not fused:
+                finish = self._search_topk_keys(queries, k, normalize_queries, scale, path)
             general = lambda: self.search_topk_general(queries, k, normalize_queries=normalize_queries,
                                                        scale=scale, path=path)
             pend = _PendingSharded(finish, general)

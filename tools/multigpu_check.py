@@ -22,6 +22,7 @@ for nq in (3, 24):
     bad = (i.cpu() != wi).sum().item()
     assert bad <= 2, (rank, nq, bad)
     assert (v.cpu() - wv).abs().max().item() < 1e-5
+assert sg._fused and sg._fused_ok, "the fused NVLink gather was not used"
 # host queries in -> host results out; asynchronous handle
 q = oracle.synthetic_queries(5, d, seed=9)
 pend = sg.search_topk(q, k, sync=False)
@@ -49,7 +50,14 @@ except mmrs_b200._cabi.MmrsError as e:
 x, planted = oracle.synthetic_dedup(30_000, 128, dup_frac=0.02, seed=5)
 pairs = sg.find_duplicate_pairs(mmrs_b200.dedup._device_f32(x, dev), 0.95)
 assert [tuple(p) for p in pairs.cpu().tolist()] == planted
+# the NCCL packed-key path must agree with the fused one
+os.environ["MMRS_NO_FUSED_GATHER"] = "1"
+sg_nccl = mmrs_b200.ShardedGallery(sg.local, n)
+q = oracle.synthetic_queries(7, d, seed=21).to(dev)
+v_a, i_a = sg.search_topk(q, k)
+v_b, i_b = sg_nccl.search_topk(q, k)
+assert torch.equal(i_a, i_b) and torch.equal(v_a, v_b) and not sg_nccl._fused
 dist.barrier()
 if rank == 0:
-    print(f"multigpu ok: world={world}")
+    print(f"multigpu ok: world={world} (fused NVLink gather + NCCL path agree)")
 dist.destroy_process_group()
