@@ -43,13 +43,14 @@ L2_BYTES = 126 * 1024 * 1024
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=ROWS_PER_GPU)
     ap.add_argument("--dim", type=int, default=DIM)
     ap.add_argument("--k", type=int, default=TOPK)
     ap.add_argument("--batch", type=int, default=Q_PER_GPU, help="queries per GPU per step")
+    ap.add_argument("--global-batch", type=int, default=0, help="total queries per step (overrides --batch x gpus)")
     ap.add_argument("--path", default="auto", choices=["auto", "gemv", "mma"])
     ap.add_argument("--sweep", action="store_true", help="also time batch sizes 1..256 (N=1, extra key)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -76,7 +77,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -152,7 +153,7 @@ def run_reference(args):
     import torch
     from oracle import oracle
     world = args.gpus
-    nq = args.batch * world
+    nq = args.global_batch or args.batch * world
     rows = args.rows     # bounded sample: one GPU's shard; the CPU rate is linear in rows
     torch.set_num_threads(os.cpu_count() or 1)
     g = oracle.synthetic_gallery(rows, args.dim, seed=0, dtype=torch.bfloat16).to(torch.float32)
@@ -187,8 +188,10 @@ def run_reference(args):
 
 
 def workload_config(args, world):
-    return {"workload": "C2: 1M x 512 bf16 gallery per GPU, top-100 cosine", "rows_per_gpu": args.rows,
-            "global_rows": args.rows * world, "dim": args.dim, "k": args.k, "queries_per_step": args.batch * world,
+    name = "C2: 1M x 512 bf16 gallery per GPU, top-100 cosine" if (args.rows, args.dim) == (ROWS_PER_GPU, DIM) \
+        else f"{args.rows} x {args.dim} bf16 gallery per GPU, top-{args.k} cosine"
+    return {"workload": name, "rows_per_gpu": args.rows,
+            "global_rows": args.rows * world, "dim": args.dim, "k": args.k, "queries_per_step": args.global_batch or args.batch * world,
             "sharding": f"rows x{world}" if world > 1 else "none",
             "l2": f"gallery shard {args.rows * args.dim * 2 / 1e9:.3f} GB streamed per step > 126 MB L2 (no flush needed)"}
 
@@ -213,7 +216,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
 
-    nq = args.batch * world
+    nq = args.global_batch or args.batch * world
     lib = _cabi.lib
     shard = device_gallery_shard(torch, args.rows, args.dim, seed=0, rank=rank, device=device)
     gal = mmrs_b200.DeviceGallery(shard, row_offset=rank * args.rows)
@@ -295,7 +298,7 @@ def main():
     torch.cuda.synchronize()
     lib.mmrs_profile_enable(0)
     import ctypes as C
-    cap = 64 * args.steps + 64
+    cap = (int(launches) // max(args.steps, 1) + 2) * args.steps + 64
     ms = (C.c_float * cap)(); kind = (C.c_int32 * cap)(); nbytes = (C.c_int64 * cap)(); flops = (C.c_int64 * cap)()
     nrec = lib.mmrs_profile_read(ms, kind, nbytes, flops, cap)
     t = torch.tensor([ms_total], device=device)
@@ -330,7 +333,21 @@ def main():
             tj = json.loads(tpath.read_text()).get(kname)
             if tj:
                 traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+        per_pass_q = min(nq, 256)
+        if per_pass_q >= 224:     # past the ridge (Q* ~ 206-248): tensor-bound
+            long_step = ms_total / args.steps > 50.0
+            peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
+            tpk = peaks.get("bf16_tflops_sustained", 1400.0) if long_step else tc_peak
+            tfl = dom[0][3] / (avg_ms / 1e3) / 1e12
+            roofline = {"bound": "tensor", "achieved": tfl, "peak": tpk, "unit": "TFLOP/s", "frac": tfl / tpk, "traffic": None,
+                        "peak_source": f"{peak_src} (MEASURED_PEAKS.json bf16_tflops{'_sustained' if long_step else ''})",
+                        "kernel": kname, "algorithmic_flops_per_launch": dom[0][3], "avg_launch_ms": avg_ms,
+                        "launches_timed": len(dom), "hbm_gbs": achieved,
+                        "whole_step_tflops": 2.0 * nq * args.rows * args.dim / (ms_total / args.steps / 1e3) / 1e12,
+                        "how": "CUDA events around every launch of the kernel, on the launching stream, over the same "
+                               f"{args.steps} steps re-run with the library's profiling hooks enabled"}
+        else:
+          roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                     "traffic": traffic, "peak_source": f"{peak_src} (MEASURED_PEAKS.json hbm_gbs, burst copy)",
                     "kernel": kname,
                     "algorithmic_bytes_per_launch": big, "avg_launch_ms": avg_ms, "launches_timed": len(dom),

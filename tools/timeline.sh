@@ -4,6 +4,6 @@ for B in ${BATCHES:-1 4 16 64 128 256}; do timeout 300 python bench.py --steps 3
 import sys,json
 for l in sys.stdin:
     if l.startswith('{'):
-        d=json.loads(l); print('batch', d['config']['queries_per_step'], 'step ms', round(d['ms_per_step'],4), 'e2e ms', round(d['e2e']['ms_per_step'],4), 'qps', int(d['value']), 'hbm_frac_step', round(d['roofline']['whole_step_frac'],3)); print('   ', [(t['kernel'], round(t['ms']*1000,1)) for t in d['kernel_timeline_ms']])
+        d=json.loads(l); print('batch', d['config']['queries_per_step'], 'step ms', round(d['ms_per_step'],4), 'e2e ms', round(d['e2e']['ms_per_step'],4), 'qps', int(d['value']), 'hbm_frac_step', round(d['roofline'].get('whole_step_frac', d['roofline'].get('frac')),3)); print('   ', [(t['kernel'], round(t['ms']*1000,1)) for t in d['kernel_timeline_ms']])
     elif 'Error' in l or 'error' in l: print(l.rstrip())
 "; done
