@@ -16,7 +16,8 @@ DeviceGallery, ShardedGallery.  Everything computes through the C-ABI CUDA libra
 from . import _cabi  # noqa: F401  (fails loudly when the CUDA library is missing)
 from .gallery import DeviceGallery, load_feature_cache
 from .search import (construct_dataset, eval_threshold, find_thresholds, full_scores,
-                     get_similarity, search_topk, threshold_sweep_counts)
+                     get_similarity, mix_image_text_query, outlier_filter_features, search_topk,
+                     threshold_sweep_counts)
 from .dedup import (find_and_remove_duplicate_images, find_duplicate_pairs,
                     find_and_remove_near_duplicate_images, get_all_images, greedy_first_keeper)
 from .sharded import ShardedGallery, shard_bounds
@@ -25,6 +26,7 @@ __all__ = [
     "DeviceGallery", "ShardedGallery", "construct_dataset", "eval_threshold", "find_thresholds",
     "find_and_remove_duplicate_images", "find_and_remove_near_duplicate_images",
     "find_duplicate_pairs", "full_scores", "get_all_images", "get_similarity",
-    "greedy_first_keeper", "load_feature_cache", "search_topk", "shard_bounds",
+    "greedy_first_keeper", "load_feature_cache", "mix_image_text_query", "outlier_filter_features",
+    "search_topk", "shard_bounds",
     "threshold_sweep_counts",
 ]

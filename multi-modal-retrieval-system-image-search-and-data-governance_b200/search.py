@@ -220,6 +220,25 @@ def construct_dataset(feature_dict, sample_images, class_name):
     return test_features, targets
 
 
+# ---- query construction on cached features ---------------------------
+def outlier_filter_features(image_features, keep_percentile: float = 95):
+    """The arithmetic of `outlier_filter` (code/search_image.py:310-318) on already encoded,
+    unit-norm sample features [S, D] (the CLIP forward of :296-309 is the caller's): mean of the
+    samples whose cosine distance to the global mean is within the 95th percentile.  The result is
+    NOT re-normalised, as in the reference.  S is ~10: host numpy, like the reference."""
+    f = np.asarray(image_features.detach().cpu() if isinstance(image_features, torch.Tensor) else image_features)
+    center = np.mean(f, axis=0)
+    cos_distances = 1 - f @ center
+    keep_mask = cos_distances <= np.percentile(cos_distances, keep_percentile)
+    return torch.tensor(np.mean(f[keep_mask], axis=0))
+
+
+def mix_image_text_query(image_prototype, text_embedding):
+    """`(robust_features + class_embeddings[c]) / 2` (code/search_image.py:387): the query handed to
+    get_similarity; un-normalised on purpose."""
+    return (torch.as_tensor(image_prototype) + torch.as_tensor(text_embedding)) / 2
+
+
 # ---- threshold sweep (SURVEY.md section 8 row f2) ---------------------------------------------------
 def threshold_sweep_counts(pos_res, neg_res, thresholds, device: Optional[torch.device] = None):
     """(tp [T], fp [T]) int64 numpy: tp[t] = #{pos >= thresholds[t]}, fp likewise, on the GPU.

@@ -138,6 +138,17 @@ def get_similarity(features: torch.Tensor, targets: np.ndarray, label: int, ref_
 
 
 # --------------------------------------------------------------------------------------------
+# query construction arithmetic: code/search_image.py:310-318 (outlier_filter, after the CLIP
+# forward) and :387 (mix with the text embedding)
+# --------------------------------------------------------------------------------------------
+def outlier_filter_features(image_features: np.ndarray) -> torch.Tensor:
+    center = np.mean(image_features, axis=0)
+    cos_distances = 1 - image_features @ center
+    keep_mask = cos_distances <= np.percentile(cos_distances, 95)
+    return torch.tensor(np.mean(image_features[keep_mask], axis=0))
+
+
+# --------------------------------------------------------------------------------------------
 # eval_threshold / find_thresholds: code/search_image.py:39-79 (plotting at :81-102 omitted)
 # --------------------------------------------------------------------------------------------
 def eval_threshold(pos_res, neg_res, threshold):

@@ -119,3 +119,16 @@ def test_construct_dataset_host_logic(mm, tmp_path, monkeypatch):
     feats, targets = S.construct_dataset(fd, ["1.jpg"], "b")
     assert feats.shape == (5, 4) and targets.tolist().count(1) == 2 and targets.tolist().count(0) == 3
     assert 11.0 not in feats[:, 0].tolist()
+
+
+def test_query_construction_helpers(mm, oracle):
+    rng = np.random.default_rng(4)
+    f = rng.standard_normal((10, 64)).astype(np.float32)
+    f[3] = -f[0]                                   # an outlier: far from the mean direction
+    f /= np.linalg.norm(f, axis=1, keepdims=True)
+    want = oracle.outlier_filter_features(f)
+    got = mm.outlier_filter_features(torch.from_numpy(f))
+    assert torch.equal(got, want)
+    assert abs(float(got.norm()) - 1.0) > 1e-3     # un-normalised, as in the reference (M3)
+    text = torch.from_numpy(rng.standard_normal(64).astype(np.float32))
+    assert torch.equal(mm.mix_image_text_query(got, text), (want + text) / 2)
