@@ -270,6 +270,21 @@ int mmrs_threshold_sweep(const float* d_pos, int64_t n_pos, const float* d_neg, 
                          int64_t* d_out_counts, void* d_workspace, size_t workspace_bytes,
                          void* stream);
 
+/*
+ * The same sweep without any N-sized host traffic: d_scores [n] fp32 and d_targets [n] int64 stay on
+ * the device, positives are the rows with target == label, the threshold grid is
+ * np.linspace(min(scores), max(scores), n_thresholds) built on the device exactly as numpy builds it
+ * (code/search_image.py:59-61) -- grid_f32 != 0: in float32 as NumPy >= 2 does for float32 scores
+ * (NEP 50), grid_f32 == 0: in float64 as NumPy 1.x did -- and returned in d_out_thresholds
+ * [n_thresholds] (fp64 either way);
+ * d_out_counts as above.  Workspace: mmrs_threshold_sweep_workspace_bytes(n_thresholds) + 256.
+ */
+int mmrs_threshold_sweep_labeled(const float* d_scores, const int64_t* d_targets, int64_t label,
+                                 int64_t n, int32_t n_thresholds, int32_t grid_f32,
+                                 double* d_out_thresholds,
+                                 int64_t* d_out_counts, void* d_workspace, size_t workspace_bytes,
+                                 void* stream);
+
 /* ---- measurement hooks (bench.py; not needed by a product caller) --------------------------- */
 
 /* Number of kernels this library has launched in this process (monotonic). */

@@ -15,7 +15,7 @@ DeviceGallery, ShardedGallery.  Everything computes through the C-ABI CUDA libra
 """
 from . import _cabi  # noqa: F401  (fails loudly when the CUDA library is missing)
 from .gallery import DeviceGallery, load_feature_cache
-from .search import (construct_dataset, eval_threshold, find_thresholds, full_scores,
+from .search import (best_threshold_on_device, construct_dataset, eval_threshold, find_thresholds, full_scores,
                      get_similarity, mix_image_text_query, outlier_filter_features, search_topk,
                      threshold_sweep_counts)
 from .dedup import (find_and_remove_duplicate_images, find_duplicate_pairs,
@@ -23,7 +23,7 @@ from .dedup import (find_and_remove_duplicate_images, find_duplicate_pairs,
 from .sharded import ShardedGallery, shard_bounds
 
 __all__ = [
-    "DeviceGallery", "ShardedGallery", "construct_dataset", "eval_threshold", "find_thresholds",
+    "DeviceGallery", "ShardedGallery", "best_threshold_on_device", "construct_dataset", "eval_threshold", "find_thresholds",
     "find_and_remove_duplicate_images", "find_and_remove_near_duplicate_images",
     "find_duplicate_pairs", "full_scores", "get_all_images", "get_similarity",
     "greedy_first_keeper", "load_feature_cache", "mix_image_text_query", "outlier_filter_features",

@@ -75,6 +75,7 @@ SIGNATURES = {
     "mmrs_launch_count": (_i64, []),
     "mmrs_profile_enable": (C.c_int, [C.c_int]),
     "mmrs_profile_read": (C.c_int, [_vp, _vp, _vp, _vp, _i32]),
+    "mmrs_threshold_sweep_labeled": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _i32, _vp, _vp, _vp, _sz, _vp]),
     "mmrs_threshold_sweep": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i32, _vp, _vp, _sz, _vp]),
 }
 for _name, (_res, _args) in SIGNATURES.items():

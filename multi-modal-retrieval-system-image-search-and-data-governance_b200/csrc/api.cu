@@ -24,6 +24,10 @@ cudaError_t launch_selfjoin_f32(const float* emb, int64_t n_rows, int32_t dim, i
 cudaError_t launch_threshold_sweep(const float* pos, int64_t n_pos, const float* neg, int64_t n_neg,
                                    const double* thr, int32_t n_thr, int64_t* out_counts,
                                    unsigned long long* hist_ws, int sm_count, cudaStream_t stream);
+cudaError_t launch_threshold_sweep_labeled(const float* scores, const int64_t* targets, int64_t label, int64_t n,
+                                           int32_t n_thr, int32_t grid_f32, double* thr_out, int64_t* out_counts,
+                                           unsigned long long* hist_ws, uint32_t* mm_ws, int sm_count,
+                                           cudaStream_t stream);
 // K5 on tensor cores (selfjoin_mma.cu)
 int64_t sjm_plan(int64_t n_rows, int32_t rank, int32_t world, int64_t* h_panel_start, int32_t max_panels,
                  int32_t* n_my_panels);
@@ -1031,6 +1035,24 @@ int mmrs_threshold_sweep(const float* d_pos, int64_t n_pos, const float* d_neg, 
   MMRS_LAUNCH(launch_threshold_sweep(d_pos, n_pos, d_neg, n_neg, d_thresholds, n_thresholds,
                                    d_out_counts, static_cast<unsigned long long*>(d_workspace),
                                    dev.sm_count, stream));
+  return MMRS_OK;
+}
+
+int mmrs_threshold_sweep_labeled(const float* d_scores, const int64_t* d_targets, int64_t label, int64_t n,
+                                 int32_t n_thresholds, int32_t grid_f32, double* d_out_thresholds, int64_t* d_out_counts,
+                                 void* d_workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceInfo dev;
+  int rc = current_device(&dev);
+  if (rc != MMRS_OK) return rc;
+  if (n_thresholds < 1 || n_thresholds > 4096) return fail(MMRS_ERR_ARG, "n_thresholds must be in [1, 4096]");
+  if (n < 1 || !d_scores || !d_targets || !d_out_thresholds || !d_out_counts) return fail(MMRS_ERR_ARG, "bad arguments");
+  if (!d_workspace || workspace_bytes < mmrs_threshold_sweep_workspace_bytes(n_thresholds) + 256)
+    return fail(MMRS_ERR_WORKSPACE, "workspace too small (need mmrs_threshold_sweep_workspace_bytes + 256)");
+  char* b = static_cast<char*>(d_workspace);
+  MMRS_LAUNCH(launch_threshold_sweep_labeled(d_scores, d_targets, label, n, n_thresholds, grid_f32, d_out_thresholds,
+                                             d_out_counts, reinterpret_cast<unsigned long long*>(b + 256),
+                                             reinterpret_cast<uint32_t*>(b), dev.sm_count, stream));
   return MMRS_OK;
 }
 

@@ -162,6 +162,77 @@ __global__ void __launch_bounds__(256) sweep_hist_kernel(const float* __restrict
     if (s_hist[i]) atomicAdd(&hist[i], static_cast<unsigned long long>(s_hist[i]));
 }
 
+// ---- fully device-resident variant: scores [n] + integer targets [n], positives = (target == label) ----
+// min / max of the scores -> np.linspace(min, max, T) in fp64 exactly as numpy builds it
+// (y = arange(T) * step + start with a separately rounded multiply and add, last point = stop) ->
+// the same histogram.  Nothing of size N leaves the GPU (code/search_image.py:109 copies all N scores).
+__device__ __forceinline__ uint32_t f2ord(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t o) {
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+__global__ void __launch_bounds__(256) minmax_kernel(const float* __restrict__ x, int64_t n, uint32_t* mm /*[2] ordered*/) {
+  uint32_t lo = 0xffffffffu, hi = 0u;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const uint32_t o = f2ord(x[i] + 0.0f);
+    lo = o < lo ? o : lo;
+    hi = o > hi ? o : hi;
+  }
+  lo = __reduce_min_sync(0xffffffffu, lo);
+  hi = __reduce_max_sync(0xffffffffu, hi);
+  if ((threadIdx.x & 31) == 0) { atomicMin(mm, lo); atomicMax(mm + 1, hi); }
+}
+// grid_f32 != 0: NumPy >= 2 semantics (NEP 50): np.linspace of two float32 scalars is computed and
+// returned in float32 (delta, step, t * step and + start each rounded to fp32); grid_f32 == 0: NumPy 1.x
+// semantics, everything in fp64.  Either way multiply and add are rounded separately (no FMA).
+__global__ void linspace_kernel(const uint32_t* __restrict__ mm, int32_t n_thr, int32_t grid_f32,
+                                double* __restrict__ thr) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_thr) return;
+  const float start32 = ord2f(mm[0]), stop32 = ord2f(mm[1]);
+  double v = static_cast<double>(start32);
+  if (n_thr > 1) {
+    if (t == n_thr - 1) {
+      v = static_cast<double>(stop32);
+    } else if (grid_f32) {
+      const float step = __fdiv_rn(__fsub_rn(stop32, start32), static_cast<float>(n_thr - 1));
+      v = static_cast<double>(__fadd_rn(__fmul_rn(static_cast<float>(t), step), start32));
+    } else {
+      const double start = static_cast<double>(start32), stop = static_cast<double>(stop32);
+      const double step = __ddiv_rn(__dsub_rn(stop, start), static_cast<double>(n_thr - 1));
+      v = __dadd_rn(__dmul_rn(static_cast<double>(t), step), start);
+    }
+  }
+  thr[t] = v;
+}
+__global__ void __launch_bounds__(256) sweep_hist_labeled_kernel(const float* __restrict__ scores,
+                                                                 const int64_t* __restrict__ targets, int64_t label,
+                                                                 int64_t n, const double* __restrict__ thr,
+                                                                 int32_t n_thr, unsigned long long* __restrict__ hist) {
+  extern __shared__ double s_thr[];
+  uint32_t* s_hist = reinterpret_cast<uint32_t*>(s_thr + n_thr);
+  for (int i = threadIdx.x; i < n_thr; i += blockDim.x) s_thr[i] = thr[i];
+  for (int i = threadIdx.x; i < 2 * (n_thr + 1); i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const bool is_neg = targets[i] != label;
+    const double x = static_cast<double>(scores[i]);
+    int lo = 0, hi = n_thr;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (x >= s_thr[mid]) lo = mid + 1; else hi = mid;
+    }
+    atomicAdd(&s_hist[(is_neg ? n_thr + 1 : 0) + lo], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * (n_thr + 1); i += blockDim.x)
+    if (s_hist[i]) atomicAdd(&hist[i], static_cast<unsigned long long>(s_hist[i]));
+}
+
 __global__ void sweep_suffix_kernel(const unsigned long long* __restrict__ hist, int32_t n_thr,
                                     int64_t* __restrict__ out) {
   // one thread per class (pos / neg): counts[t] = sum_{b > t} hist[b]
@@ -192,6 +263,32 @@ cudaError_t launch_threshold_sweep(const float* pos, int64_t n_pos, const float*
   sweep_hist_kernel<<<static_cast<int>(grid), 256, smem, stream>>>(pos, n_pos, neg, n_neg, thr, n_thr, hist_ws);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
+  sweep_suffix_kernel<<<1, 32, 0, stream>>>(hist_ws, n_thr, out_counts);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_threshold_sweep_labeled(const float* scores, const int64_t* targets, int64_t label, int64_t n,
+                                           int32_t n_thr, int32_t grid_f32, double* thr_out, int64_t* out_counts,
+                                           unsigned long long* hist_ws, uint32_t* mm_ws, int sm_count,
+                                           cudaStream_t stream) {
+  if (n_thr < 1 || n_thr > kSweepMaxT || n < 1) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemsetAsync(hist_ws, 0, sizeof(unsigned long long) * 2 * (n_thr + 1), stream);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(mm_ws, 0xff, sizeof(uint32_t), stream);           // min <- 0xffffffff
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(mm_ws + 1, 0, sizeof(uint32_t), stream);          // max <- 0
+  if (e != cudaSuccess) return e;
+  int64_t grid = (n + 256 * 8 - 1) / (256 * 8);
+  if (grid > sm_count * 4) grid = sm_count * 4;
+  if (grid < 1) grid = 1;
+  minmax_kernel<<<static_cast<int>(grid), 256, 0, stream>>>(scores, n, mm_ws);
+  linspace_kernel<<<(n_thr + 255) / 256, 256, 0, stream>>>(mm_ws, n_thr, grid_f32, thr_out);
+  const size_t smem = sizeof(double) * n_thr + sizeof(uint32_t) * 2 * (n_thr + 1);
+  e = cudaFuncSetAttribute(sweep_hist_labeled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           static_cast<int>(sizeof(double) * kSweepMaxT + sizeof(uint32_t) * 2 * (kSweepMaxT + 1)));
+  if (e != cudaSuccess) return e;
+  sweep_hist_labeled_kernel<<<static_cast<int>(grid), 256, smem, stream>>>(scores, targets, label, n, thr_out, n_thr,
+                                                                            hist_ws);
   sweep_suffix_kernel<<<1, 32, 0, stream>>>(hist_ws, n_thr, out_counts);
   return cudaGetLastError();
 }

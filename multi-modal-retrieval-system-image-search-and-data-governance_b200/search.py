@@ -279,6 +279,40 @@ def _f1_from_counts(tp, fp, n_pos):
     return f1, precision, recall
 
 
+def best_threshold_on_device(scores: torch.Tensor, targets, label, n_points: int = 200):
+    """find_thresholds (code/search_image.py:58-79) for scores that never leave the GPU: `scores` is a
+    CUDA fp32 vector (e.g. one row of full_scores), `targets` the class ids.  Returns
+    (best_f1, best_threshold, best_precision, best_recall, thresholds, f1_scores); only the
+    n_points-sized grid and counts are copied to the host."""
+    dev = scores.device
+    _cabi.require_b200(dev.index or 0)
+    s = scores.detach().to(torch.float32).contiguous().reshape(-1)
+    t = torch.as_tensor(np.asarray(targets) if not isinstance(targets, torch.Tensor) else targets)
+    t = t.to(device=dev, dtype=torch.int64).contiguous().reshape(-1)
+    if t.numel() != s.numel():
+        raise ValueError("scores and targets differ in length")
+    lib = _cabi.lib
+    with torch.cuda.device(dev):
+        thr = torch.empty(n_points, dtype=torch.float64, device=dev)
+        out = torch.empty((n_points, 2), dtype=torch.int64, device=dev)
+        ws_bytes = lib.mmrs_threshold_sweep_workspace_bytes(n_points) + 256
+        ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=dev)
+        # the grid follows the installed numpy: float32 under NEP 50 (NumPy >= 2), float64 before
+        grid_f32 = int(np.linspace(np.float32(0), np.float32(1), 3).dtype == np.float32)
+        _cabi.check(lib.mmrs_threshold_sweep_labeled(s.data_ptr(), t.data_ptr(), int(label), s.numel(), n_points,
+                                                     grid_f32, thr.data_ptr(), out.data_ptr(), DeviceGallery.aligned_ptr(ws),
+                                                     ws_bytes, _stream_handle(dev)))
+        n_pos = int((t == int(label)).sum().item())
+        counts = out.cpu().numpy()
+        thresholds = thr.cpu().numpy()
+    f1s, ps, rs = _f1_from_counts(counts[:, 0], counts[:, 1], n_pos)
+    best = (0., 0., 0., 0.)
+    for th, f1, p, r in zip(thresholds, f1s, ps, rs):
+        if f1 > best[0]:                      # first strict maximum wins (:74)
+            best = (f1, th, p, r)
+    return best[0], best[1], best[2], best[3], thresholds, f1s
+
+
 def eval_threshold(pos_res, neg_res, threshold):
     """Drop-in for code/search_image.py:39-56 -> (f1_score, precision, recall)."""
     tp, fp = threshold_sweep_counts(pos_res, neg_res, [threshold])

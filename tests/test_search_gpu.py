@@ -353,3 +353,19 @@ def test_async_search_handles(mm, oracle):
         assert torch.equal(i, wi) and torch.equal(v, wv)
     pd = mm.search_topk(qs[0].cuda(), gal, 20, sync=False)
     assert torch.equal(pd.wait()[1].cpu(), pend[0].wait()[1])
+
+
+def test_device_resident_threshold_sweep(mm, oracle):
+    """f2: scores stay on the GPU; grid, counts and best F1 equal the reference's find_thresholds."""
+    gold = np.load(GOLDEN / "search_image_golden.npz")
+    for name, (features, targets, label, ref) in similarity_inputs().items():
+        gal = mm.DeviceGallery(features, mode="fp32")
+        scores = mm.full_scores(ref[None].cuda(), gal, normalize_queries=False, scale=100.0)[0]   # CUDA [N]
+        best_f1, best_thr, p, r, thresholds, f1s = mm.best_threshold_on_device(scores, targets, label)
+        s_host = scores.cpu().numpy()
+        want = oracle.find_thresholds(s_host[targets == label], s_host[targets != label])
+        np.testing.assert_array_equal(thresholds, want[4])           # the linspace grid, bit for bit
+        np.testing.assert_array_equal(f1s, want[5])
+        assert (best_f1, best_thr) == (want[0], want[1])
+        # and against the recorded output of the reference's own function (scores differ by <= 1e-3)
+        assert abs(best_f1 - float(gold[f"{name}_best_f1"])) < 0.02
