@@ -269,3 +269,55 @@ def find_and_remove_duplicate_images(reference_folder, delete_folder=None, *, em
         thr = 0.95 if delete_folder is None else float(delete_folder)
         return find_and_remove_near_duplicate_images(reference_folder, thr, embed=embed, dry_run=dry_run)
     return _cross_folder(reference_folder, delete_folder, embed or pixel_embedding, threshold, dry_run)
+
+
+CROSS_SET_EXTENSIONS = ['.jpg', '.jpeg', '.png', '.bmp', '.gif', '.webp']   # tool/delete repeated.py:35
+last_cross_set_summary: dict = {}
+
+
+def detect_and_remove_cross_set_duplicates(test_dir, train_dir, hash_size=8, similarity_threshold=0, *,
+                                           embed: Optional[Embedder] = None, cosine_threshold: float = 0.9999,
+                                           dry_run: bool = False):
+    """Drop-in for `tool/delete repeated.py`:11-162 (train-vs-test leakage removal): every image of
+    `train_dir` that matches an image of `test_dir` is deleted from `train_dir`; prints the same
+    summary and returns None like the reference (the numbers are kept in `last_cross_set_summary`).
+    `hash_size` / `similarity_threshold` are the reference's dHash parameters and are accepted for
+    signature compatibility; the predicate here is cos(e_train, e_test) >= `cosine_threshold`
+    (top-1 search of the train embeddings against the test gallery)."""
+    del hash_size, similarity_threshold
+    for d, name in ((test_dir, "测试集"), (train_dir, "训练集")):
+        if not os.path.exists(d):
+            print(f"错误: {name}目录 '{d}' 不存在。")
+            return
+
+    def listing(folder):
+        out = []
+        for root, _, files in os.walk(folder):
+            out.extend(os.path.join(root, f) for f in files if os.path.splitext(f)[1].lower() in CROSS_SET_EXTENSIONS)
+        return out
+
+    embed = embed or pixel_embedding
+    test_images, train_images = listing(test_dir), listing(train_dir)
+    test_emb, test_ok = embed(test_images)
+    train_emb, train_ok = embed(train_images)
+    test_paths = [p for p, ok in zip(test_images, test_ok) if ok]
+    duplicates_found = deleted_files = 0
+    if len(test_paths) and train_emb.shape[0]:
+        vals, idx = search_topk(train_emb, DeviceGallery(test_emb, mode="fp32"), 1, normalize_queries=False)
+        ok_pos = np.flatnonzero(train_ok)
+        for row, (v, i) in enumerate(zip(vals.cpu().numpy()[:, 0], idx.cpu().numpy()[:, 0])):
+            if v >= cosine_threshold:
+                duplicates_found += 1
+                path = train_images[ok_pos[row]]
+                print(f"\n发现重复图片 #{duplicates_found}:\n测试集: {test_paths[int(i)]}\n训练集: {path}")
+                if _remove(path, dry_run):
+                    deleted_files += 1
+    last_cross_set_summary.clear()
+    last_cross_set_summary.update(test_images=len(test_images), train_images=len(train_images),
+                                  duplicates_found=duplicates_found, deleted_files=deleted_files)
+    print("\n====== 操作摘要 ======")
+    print(f"测试集图片数: {len(test_images)}")
+    print(f"训练集图片数: {len(train_images)}")
+    print(f"发现的重复图片数: {duplicates_found}")
+    print(f"已删除的训练集重复图片: {deleted_files}")
+    print("=====================")

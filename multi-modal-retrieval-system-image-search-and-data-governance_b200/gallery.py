@@ -104,6 +104,21 @@ class DeviceGallery:
         p = buf.data_ptr()
         return (p + 255) // 256 * 256
 
+    def lookup_paths(self, indices):
+        """Relative paths (the keys of the reference's feature pickle, search_image.py:157) of the
+        rows a search returned; `indices` are global ids (row_offset already added)."""
+        if self.paths is None:
+            raise ValueError("this gallery was built without a path table")
+        idx = indices.detach().cpu().numpy() if isinstance(indices, torch.Tensor) else np.asarray(indices)
+        flat = [self.paths[int(i) - self.row_offset] for i in idx.reshape(-1)]
+        return np.array(flat, dtype=object).reshape(idx.shape).tolist()
+
+    @classmethod
+    def from_feature_cache(cls, path: str, mode: Optional[str] = None, device=None) -> "DeviceGallery":
+        """Resident gallery straight from the reference's cache file (pickle dict or .pt tensor)."""
+        feats, keys = load_feature_cache(path)
+        return cls(feats, mode=mode, device=device, paths=keys)
+
     def __len__(self) -> int:
         return self.n_rows
 

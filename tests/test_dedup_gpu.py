@@ -128,3 +128,32 @@ def test_tc_buffers_regrow(mm, oracle):
     from mmrs_b200.dedup import selfjoin_tc_raw, sort_pairs, _device_f32
     got = sort_pairs(selfjoin_tc_raw(_device_f32(x), 0.05, capacity=16), 3000).cpu()   # thousands of pairs
     assert torch.equal(got, oracle.dedup_pairs(x, 0.05))
+
+
+def test_cross_set_leakage_wrapper(mm, tmp_path, capsys):
+    """tool/delete repeated.py signature: train images that match a test image are deleted; returns None."""
+    ref_dir, del_dir = dedup_image_set(str(tmp_path))       # reference = "test set", delete = "train set"
+    before = set(mm.get_all_images(del_dir))
+    out = mm.detect_and_remove_cross_set_duplicates(ref_dir, del_dir, 8, 0)
+    assert out is None
+    from mmrs_b200.dedup import last_cross_set_summary as s
+    # this tool's extension list has .webp but no .tiff (delete repeated.py:35): d.tiff is not part of the
+    # test set, so d_copy.png stays
+    assert s["test_images"] == 4 and s["train_images"] == 7
+    assert s["duplicates_found"] == 2 and s["deleted_files"] == 2
+    after = set(mm.get_all_images(del_dir))
+    assert {os.path.basename(p) for p in before - after} == {"a_copy.bmp", "c_copy.png"}
+    assert "操作摘要" in capsys.readouterr().out
+    assert mm.detect_and_remove_cross_set_duplicates(str(tmp_path / "missing"), del_dir) is None
+
+
+def test_gallery_from_feature_cache_and_path_lookup(mm, oracle, tmp_path):
+    import pickle
+    g = oracle.synthetic_gallery(300, 64, seed=2, dtype=torch.float32)
+    d = {f"cls{i % 3}/{i}.jpg": g[i].numpy() for i in range(300)}
+    with open(tmp_path / "features.pkl", "wb") as f:
+        pickle.dump(d, f)                                   # the format of search_image.py:159-160
+    gal = mm.DeviceGallery.from_feature_cache(str(tmp_path / "features.pkl"))
+    v, i = mm.search_topk(g[7:9], gal, 3)
+    paths = gal.lookup_paths(i)
+    assert paths[0][0] == "cls1/7.jpg" and paths[1][0] == "cls2/8.jpg" and abs(float(v[0, 0]) - 1.0) < 1e-5
