@@ -69,6 +69,10 @@ extern "C" {
 /* element types of the gallery / embedding matrix */
 #define MMRS_DTYPE_F32 0
 #define MMRS_DTYPE_BF16 1
+#define MMRS_DTYPE_BF16X3 2 /* an fp32 matrix stored as three bf16 planes hi / mid / lo (x == hi + mid + lo,
+                               plane stride n_rows * ld elements; mmrs_split_bf16x3 builds it): searched
+                               on the tensor cores with six bf16 MMAs per tile and UNROUNDED queries --
+                               fp32-mode results (scores within 1e-6) at tensor-core speed */
 
 /* kernel selection for mmrs_search_topk / mmrs_full_scores */
 #define MMRS_PATH_AUTO 0   /* K1 for small batches, K2 (tcgen05) otherwise               */
@@ -97,6 +101,10 @@ int mmrs_full_scores(const void* d_gallery, int64_t n_rows, int32_t dim, int64_t
                      int64_t ld_queries, int32_t normalize_queries, float scale, int32_t path,
                      float* d_out_scores, int64_t ld_out, void* d_workspace,
                      size_t workspace_bytes, void* stream);
+
+/* fp32 [n_rows, ld_src] -> bf16 planes [3, n_rows, ld_dst] (ld_dst % 8 == 0, >= dim; padding zeroed). */
+int mmrs_split_bf16x3(const float* d_src, int64_t n_rows, int32_t dim, int64_t ld_src, void* d_dst,
+                      int64_t ld_dst, void* stream);
 
 /* ---- search: fused top-k ------------------------------------------------------------- */
 

@@ -10,7 +10,7 @@ LIB_PATH = _PKG_DIR / "lib" / "libmmrs_b200.so"
 
 OK = 0
 ERR_ARG, ERR_CUDA, ERR_ARCH, ERR_WORKSPACE, ERR_ZERO_NORM, ERR_CAPACITY, ERR_INTERNAL, ERR_RETRY = -1, -2, -3, -4, -5, -6, -7, -8
-DTYPE_F32, DTYPE_BF16 = 0, 1
+DTYPE_F32, DTYPE_BF16, DTYPE_BF16X3 = 0, 1, 2
 PATH_AUTO, PATH_GEMV, PATH_MMA = 0, 1, 2
 PATHS = {"auto": PATH_AUTO, "gemv": PATH_GEMV, "mma": PATH_MMA}
 
@@ -45,6 +45,7 @@ SIGNATURES = {
     "mmrs_full_scores_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32]),
     "mmrs_full_scores": (C.c_int, [_vp, _i64, _i32, _i64, _i32, _vp, _i32, _i64, _i32, _f32, _i32,
                                    _vp, _i64, _vp, _sz, _vp]),
+    "mmrs_split_bf16x3": (C.c_int, [_vp, _i64, _i32, _i64, _vp, _i64, _vp]),
     "mmrs_search_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32, _i32]),
     "mmrs_search_topk": (C.c_int, [_vp, _i64, _i32, _i64, _i32, _vp, _i32, _i64, _i32, _i32, _f32,
                                    _i64, _i32, _vp, _vp, _vp, _sz, _vp]),

@@ -42,8 +42,11 @@ cudaError_t launch_selfjoin_recheck(const int64_t* cand, int64_t n_cand, const f
                                     unsigned long long* out_count, cudaStream_t stream);
 // K2.  q_bf16 is the prepared [n_q_padded, ldq] bf16 query matrix; handles up to 256 queries.
 cudaError_t launch_scan_mma(const ScanParams& p, const __nv_bfloat16* q_bf16, int32_t n_q_padded,
-                            int mode, int32_t* flags, int sm_count, cudaStream_t stream);
+                            int mode, int32_t* flags, int sm_count, cudaStream_t stream, int split);
+cudaError_t launch_split_bf16x3(const float* src, int64_t n_rows, int32_t dim, int64_t ld_src, __nv_bfloat16* dst,
+                                int64_t ld_dst, int sm_count, cudaStream_t stream);
 int scan_mma_max_queries();
+int scan_mma_split_max_queries();
 bool scan_mma_available();
 
 static thread_local char g_err[512] = "";
@@ -172,7 +175,7 @@ static Workspace carve(void* base, int64_t n_rows, int32_t dim, int32_t n_querie
   w.flags = reinterpret_cast<int32_t*>(take(8 * sizeof(int32_t)));
   w.gscratch = reinterpret_cast<uint32_t*>(take(8 * sizeof(uint32_t)));
   w.q_f32 = reinterpret_cast<float*>(take(static_cast<size_t>(qp) * ldq * sizeof(float)));
-  w.q_bf16 = reinterpret_cast<__nv_bfloat16*>(take(static_cast<size_t>(qp) * ldq * sizeof(__nv_bfloat16)));
+  w.q_bf16 = reinterpret_cast<__nv_bfloat16*>(take(3 * static_cast<size_t>(qp) * ldq * sizeof(__nv_bfloat16)));   // up to 3 planes
   if (with_lists) {
     const SearchPlan pl = plan_for(n_rows, k, n_queries);
     const int32_t qs = n_queries < kSuperChunk ? n_queries : kSuperChunk;
@@ -193,9 +196,9 @@ static int check_matrix(const void* p, int64_t n_rows, int32_t dim, int64_t ld, 
   if (!p) return fail(MMRS_ERR_ARG, "%s pointer is null", what);
   if (n_rows < 1) return fail(MMRS_ERR_ARG, "%s has %lld rows", what, (long long)n_rows);
   if (n_rows > 0xffffffffll) return fail(MMRS_ERR_ARG, "%s: more than 2^32 rows per shard", what);
-  if (dtype != MMRS_DTYPE_F32 && dtype != MMRS_DTYPE_BF16)
+  if (dtype != MMRS_DTYPE_F32 && dtype != MMRS_DTYPE_BF16 && dtype != MMRS_DTYPE_BF16X3)
     return fail(MMRS_ERR_ARG, "%s dtype %d unknown", what, dtype);
-  const int elems16 = dtype == MMRS_DTYPE_BF16 ? 8 : 4;
+  const int elems16 = dtype == MMRS_DTYPE_F32 ? 4 : 8;
   if (dim < 1 || dim % elems16 != 0)
     return fail(MMRS_ERR_ARG, "%s dim %d must be a positive multiple of %d (pad with zeros)", what,
                 dim, elems16);
@@ -219,6 +222,7 @@ static int32_t* pinned_status() {
 enum class Path { kGemv, kMma };
 
 static Path choose_path(int32_t requested, int32_t dtype, int32_t n_queries) {
+  if (dtype == MMRS_DTYPE_BF16X3) return Path::kMma;   // split planes exist for the tensor cores only
   if (requested == MMRS_PATH_GEMV) return Path::kGemv;
   if (requested == MMRS_PATH_MMA) return Path::kMma;
   // measured on B200 (profiles/r01_tune3.log): K1 wins for 1-2 queries, K2 from 3 on
@@ -248,7 +252,7 @@ static int profiled_launch(int32_t kind, int64_t bytes, int64_t flops, cudaStrea
 template <typename F>
 static int profiled_scan(int32_t kind, int32_t dtype, const ScanParams& p, cudaStream_t stream, F launch) {
   const int64_t rows = g_prof_on.load(std::memory_order_relaxed) ? rows_in_schedule(p.sched, p.n_rows) : 0;
-  return profiled_launch(kind, rows * p.dim * (dtype == MMRS_DTYPE_BF16 ? 2 : 4), 2 * rows * p.dim * p.nq,
+  return profiled_launch(kind, rows * p.dim * (dtype == MMRS_DTYPE_BF16 ? 2 : (dtype == MMRS_DTYPE_BF16X3 ? 6 : 4)), 2 * rows * p.dim * p.nq,
                          stream, launch);
 }
 
@@ -260,17 +264,19 @@ static int run_scan(Path path, const DeviceInfo& dev, int32_t dtype, ScanParams 
     // 256 queries per CTA (the UMMA N limit); when at least two full chunks remain, one launch takes
     // up to four of them and their CTAs share every gallery tile through L2 (scan_mma.cu, gridDim.y):
     // +7 % on the 64K-query C5 shard, +8 % at 1024 queries on C2
+    const int split = dtype == MMRS_DTYPE_BF16X3 ? 3 : 1;
     const int wide = scan_mma_max_queries();
     for (int32_t q = q_lo; q < q_hi;) {
       const int32_t rem = q_hi - q;
       int32_t chunk = rem < 256 ? rem : 256;
       if (rem >= 512) chunk = (rem / 256 < wide / 256 ? rem / 256 : wide / 256) * 256;   // 2..4 full chunks
+      if (split == 3) chunk = rem < scan_mma_split_max_queries() ? rem : scan_mma_split_max_queries();
       ScanParams p = base;
       p.q0 = q;
       p.nq = chunk;
       q += chunk;
       int rc = profiled_scan(MMRS_PATH_MMA, dtype, p, stream, [&]() {
-        return launch_scan_mma(p, w.q_bf16, n_q_padded, mode, w.flags, dev.sm_count, stream);
+        return launch_scan_mma(p, w.q_bf16, n_q_padded, mode, w.flags, dev.sm_count, stream, split);
       });
       if (rc != MMRS_OK) return rc;
     }
@@ -317,14 +323,15 @@ static int enqueue_search(const SearchArgs& a, const DeviceInfo& dev, const Work
   const SearchPlan pl = plan_for(a.n_rows, a.k, a.n_queries);
   const int32_t ldq = padded_dim(a.dim), qp = padded_queries(a.n_queries);
   const Path path = choose_path(a.path, a.dtype, a.n_queries);
-  if (path == Path::kMma && a.dtype != MMRS_DTYPE_BF16)
-    return fail(MMRS_ERR_ARG, "MMRS_PATH_MMA needs a bf16 gallery");
+  if (path == Path::kMma && a.dtype == MMRS_DTYPE_F32)
+    return fail(MMRS_ERR_ARG, "MMRS_PATH_MMA needs a bf16 (or bf16x3) gallery");
 
   MMRS_CUDA(cudaMemsetAsync(w.flags, 0, 8 * sizeof(int32_t), stream));
   {
     int rc = profiled_launch(4, 0, 0, stream, [&]() {
       return launch_prep_queries(a.d_queries, a.n_queries, a.ldq_in, a.dim, a.normalize,
-                                 a.dtype == MMRS_DTYPE_BF16, w.q_f32, w.q_bf16, qp, ldq, w.flags, stream);
+                                 a.dtype == MMRS_DTYPE_BF16 ? 1 : (a.dtype == MMRS_DTYPE_BF16X3 ? 2 : 0), w.q_f32, w.q_bf16, qp, ldq,
+                                 w.flags, stream);
     });
     if (rc != MMRS_OK) return rc;
   }
@@ -386,7 +393,11 @@ static int enqueue_exhaustive(const SearchArgs& a, const DeviceInfo& dev, const 
     ScanParams p = base;
     p.cand = w.cand - static_cast<int64_t>(q) * all_rows;
     p.q0 = q; p.nq = 1;
-    MMRS_LAUNCH(launch_scan_gemv(p, a.dtype, kModeDense, dev.sm_count, stream));
+    if (a.dtype == MMRS_DTYPE_BF16X3) {
+      MMRS_LAUNCH(launch_scan_mma(p, w.q_bf16, padded_queries(a.n_queries), kModeDense, w.flags, dev.sm_count, stream, 3));
+    } else {
+      MMRS_LAUNCH(launch_scan_gemv(p, a.dtype, kModeDense, dev.sm_count, stream));
+    }
     SelectParams sp{};
     sp.cand = w.cand; sp.cnt = w.cnt; sp.thr = w.thr; sp.cap = all_rows;
     sp.fixed_n = all_rows; sp.k = a.k; sp.final_pass = 1;
@@ -550,12 +561,12 @@ int mmrs_full_scores(const void* d_gallery, int64_t n_rows, int32_t dim, int64_t
   const Workspace w = carve(d_workspace, n_rows, dim, n_queries, 1, false);
   const int32_t ldq = padded_dim(dim), qp = padded_queries(n_queries);
   const Path p = choose_path(path, gallery_dtype, n_queries);
-  if (p == Path::kMma && gallery_dtype != MMRS_DTYPE_BF16)
-    return fail(MMRS_ERR_ARG, "MMRS_PATH_MMA needs a bf16 gallery");
+  if (p == Path::kMma && gallery_dtype == MMRS_DTYPE_F32)
+    return fail(MMRS_ERR_ARG, "MMRS_PATH_MMA needs a bf16 (or bf16x3) gallery");
   MMRS_CUDA(cudaMemsetAsync(w.flags, 0, 8 * sizeof(int32_t), stream));
   MMRS_LAUNCH(launch_prep_queries(d_queries, n_queries, ld_queries, dim, normalize_queries,
-                                gallery_dtype == MMRS_DTYPE_BF16, w.q_f32, w.q_bf16, qp, ldq,
-                                w.flags, stream));
+                                gallery_dtype == MMRS_DTYPE_BF16 ? 1 : (gallery_dtype == MMRS_DTYPE_BF16X3 ? 2 : 0),
+                                w.q_f32, w.q_bf16, qp, ldq, w.flags, stream));
   ScanParams base{};
   base.gallery = d_gallery; base.n_rows = n_rows; base.ld = ld_gallery; base.dim = dim;
   base.queries = w.q_f32; base.ldq = ldq; base.scale = scale;
@@ -569,6 +580,18 @@ int mmrs_full_scores(const void* d_gallery, int64_t n_rows, int32_t dim, int64_t
   MMRS_CUDA(cudaMemcpyAsync(h, w.flags, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
   MMRS_CUDA(cudaStreamSynchronize(stream));
   return flags_to_status(h[0]);
+}
+
+int mmrs_split_bf16x3(const float* d_src, int64_t n_rows, int32_t dim, int64_t ld_src, void* d_dst,
+                      int64_t ld_dst, void* stream) {
+  DeviceInfo dev;
+  int rc = current_device(&dev);
+  if (rc != MMRS_OK) return rc;
+  if (!d_src || !d_dst || n_rows < 1 || dim < 1 || ld_src < dim || ld_dst < dim || ld_dst % 8 != 0)
+    return fail(MMRS_ERR_ARG, "bad arguments (ld_dst must be a multiple of 8 and >= dim)");
+  MMRS_LAUNCH(launch_split_bf16x3(d_src, n_rows, dim, ld_src, static_cast<__nv_bfloat16*>(d_dst), ld_dst,
+                                  dev.sm_count, static_cast<cudaStream_t>(stream)));
+  return MMRS_OK;
 }
 
 size_t mmrs_search_workspace_bytes(int64_t n_rows, int32_t dim, int32_t gallery_dtype,

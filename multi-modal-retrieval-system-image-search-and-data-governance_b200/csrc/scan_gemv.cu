@@ -243,10 +243,19 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(
   for (int d = lane; d < ld_out; d += 32) {
     float v = 0.f;
     if (real && d < dim) v = normalize ? src[d] / inv_den : src[d];
-    if (round_bf16) {
+    if (round_bf16 == 1) {
       const __nv_bfloat16 b = __float2bfloat16_rn(v);
       v = __bfloat162float(b);
       if (out_bf16) out_bf16[static_cast<int64_t>(row) * ld_out + d] = b;
+    } else if (round_bf16 == 2 && out_bf16) {
+      // fp32 emulation on tensor cores: three planes hi / mid / lo with v == hi + mid + lo
+      const int64_t plane = static_cast<int64_t>(n_rows_padded) * ld_out;
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      const float r1 = v - __bfloat162float(hi);
+      const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+      const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+      const int64_t o = static_cast<int64_t>(row) * ld_out + d;
+      out_bf16[o] = hi; out_bf16[o + plane] = mid; out_bf16[o + 2 * plane] = lo;
     }
     out_f32[static_cast<int64_t>(row) * ld_out + d] = v;
   }
@@ -260,6 +269,32 @@ cudaError_t launch_prep_queries(const float* q, int32_t n_queries, int64_t ldq, 
   const int grid = (n_rows_padded + warps_per_block - 1) / warps_per_block;
   return launch_pdl(prep_queries_kernel, dim3(grid), dim3(warps_per_block * 32), 0, stream, q, n_queries,
                     ldq, dim, normalize, round_bf16, out_f32, out_bf16, n_rows_padded, ld_out, flags);
+}
+
+// ---- fp32 -> three bf16 planes (gallery ingest for the fp32 tensor-core path) ------------------------
+__global__ void __launch_bounds__(256) split_bf16x3_kernel(const float* __restrict__ src, int64_t n_rows, int32_t dim,
+                                                           int64_t ld_src, __nv_bfloat16* __restrict__ dst, int64_t ld_dst) {
+  const int64_t total = n_rows * ld_dst;
+  const int64_t plane = n_rows * ld_dst;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / ld_dst;
+    const int32_t d = static_cast<int32_t>(i % ld_dst);
+    const float v = d < dim ? src[r * ld_src + d] : 0.f;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(hi);
+    const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+    dst[i] = hi; dst[i + plane] = mid; dst[i + 2 * plane] = lo;
+  }
+}
+cudaError_t launch_split_bf16x3(const float* src, int64_t n_rows, int32_t dim, int64_t ld_src, __nv_bfloat16* dst,
+                                int64_t ld_dst, int sm_count, cudaStream_t stream) {
+  if (n_rows <= 0) return cudaSuccess;
+  int64_t grid = (n_rows * ld_dst + 255) / 256;
+  if (grid > static_cast<int64_t>(sm_count) * 16) grid = static_cast<int64_t>(sm_count) * 16;
+  split_bf16x3_kernel<<<static_cast<int>(grid), 256, 0, stream>>>(src, n_rows, dim, ld_src, dst, ld_dst);
+  return cudaGetLastError();
 }
 
 // ---- small fills ----------------------------------------------------------------------------

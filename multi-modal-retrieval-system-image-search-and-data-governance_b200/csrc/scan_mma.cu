@@ -29,6 +29,7 @@ constexpr int kBlockM = kTileRows;       // gallery rows per tile == UMMA M
 constexpr int kBlockK = 64;              // bf16 elements per k-block == one 128-byte swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kMaxQ = 256;               // UMMA N limit
+constexpr int kSplitMaxQ = 48;           // fp32 emulation: queries per pass (3 x (16 + 6) KB per stage, 3 stages)
 constexpr int kMaxQChunks = 4;           // query chunks of kMaxQ that may share the gallery stream of one launch
 constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KiB
 constexpr int kMaxStages = 8;
@@ -52,6 +53,9 @@ struct MmaCfg {
   int32_t stages;
   int32_t tmem_cols;     // power of two >= 2 * n_umma, >= 32
   int32_t acc_stride;    // column offset between the two accumulator stages
+  int32_t split;         // 1: bf16 operands; 3: fp32 emulation, operands split into hi/mid/lo bf16 planes
+  int64_t g_plane_rows;  // split == 3: rows between two planes of the gallery (= n_rows)
+  int32_t q_plane_rows;  // split == 3: rows between two planes of the prepared queries
   int32_t debug_skip_epilogue;   // measurement aid (MMRS_K2_DEBUG_SKIP_EPI=1): results are garbage
 };
 
@@ -65,7 +69,10 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
   // 1024-byte aligned for the 128-byte swizzle
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t b_bytes = static_cast<uint32_t>(cfg.n_umma) * kBlockK * 2;
-  const uint32_t stage_bytes = kABytes + b_bytes;
+  // split == 3 (fp32 emulation): a stage holds the hi/mid/lo planes of both operands,
+  // [A_hi | A_mid | A_lo | B_hi | B_mid | B_lo]
+  const uint32_t a_all = static_cast<uint32_t>(cfg.split) * kABytes;
+  const uint32_t stage_bytes = static_cast<uint32_t>(cfg.split) * (kABytes + b_bytes);
   MmaShared* sh = reinterpret_cast<MmaShared*>(ring + static_cast<size_t>(cfg.stages) * stage_bytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -133,8 +140,12 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
           if (!mbar_wait(&sh->empty[stage], phase ^ 1, &sh->abort, flags)) { ok = false; break; }
           uint8_t* a_dst = ring + static_cast<size_t>(stage) * stage_bytes;
           mbar_expect_tx(&sh->full[stage], stage_bytes);
-          tma_load_2d(a_dst, &map_g, &sh->full[stage], kb * kBlockK, row0, kEvictFirst);
-          tma_load_2d(a_dst + kABytes, &map_q, &sh->full[stage], kb * kBlockK, q0, kEvictLast);
+          for (int pl = 0; pl < cfg.split; ++pl) {
+            tma_load_2d(a_dst + pl * kABytes, &map_g, &sh->full[stage], kb * kBlockK,
+                        static_cast<int32_t>(pl * cfg.g_plane_rows) + row0, kEvictFirst);
+            tma_load_2d(a_dst + a_all + pl * b_bytes, &map_q, &sh->full[stage], kb * kBlockK,
+                        pl * cfg.q_plane_rows + q0, kEvictLast);
+          }
           if (++stage == static_cast<uint32_t>(cfg.stages)) { stage = 0; phase ^= 1; }
         }
       }
@@ -156,14 +167,31 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
           if (!mbar_wait(&sh->full[stage], phase, &sh->abort, flags)) { ok = false; break; }
           tcgen05_fence_after();
           const uint32_t a_addr = smem_u32(ring + static_cast<size_t>(stage) * stage_bytes);
-          const uint64_t adesc = make_sw128_desc(a_addr);
-          const uint64_t bdesc = make_sw128_desc(a_addr + kABytes);
+          if (cfg.split == 1) {
+            const uint64_t adesc = make_sw128_desc(a_addr);
+            const uint64_t bdesc = make_sw128_desc(a_addr + kABytes);
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            // advancing 16 bf16 along K inside the swizzled 128-byte row = +32 bytes = +2 in the
-            // (>>4) start-address field
-            umma_bf16(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
-                      (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              // advancing 16 bf16 along K inside the swizzled 128-byte row = +32 bytes = +2 in the
+              // (>>4) start-address field
+              umma_bf16(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
+                        (kb | k) != 0 ? 1u : 0u);
+            }
+          } else {
+            // fp32 emulation: x = hi + mid + lo (three bf16, 24 mantissa bits, exact), and
+            // g.q ~ g_hi(q_hi + q_mid + q_lo) + g_mid(q_hi + q_mid) + g_lo q_hi: six bf16 MMAs into one
+            // fp32 accumulator; the dropped terms are below 2^-24 of |g||q|.
+            constexpr int kTermA[6] = {0, 0, 1, 0, 1, 2};
+            constexpr int kTermB[6] = {0, 1, 0, 2, 1, 0};
+#pragma unroll
+            for (int term = 0; term < 6; ++term) {
+              const uint64_t adesc = make_sw128_desc(a_addr + kTermA[term] * kABytes);
+              const uint64_t bdesc = make_sw128_desc(a_addr + a_all + kTermB[term] * b_bytes);
+#pragma unroll
+              for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                umma_bf16(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
+                          (kb | k | term) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(&sh->empty[stage]);   // smem slot reusable once these MMAs retire
           if (++stage == static_cast<uint32_t>(cfg.stages)) { stage = 0; phase ^= 1; }
@@ -314,6 +342,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
   }
 }
 
+int scan_mma_split_max_queries() { return kSplitMaxQ; }
 int scan_mma_max_queries() {
   const char* e = getenv("MMRS_K2_QCHUNKS");
   const int c = e ? atoi(e) : kMaxQChunks;
@@ -322,9 +351,11 @@ int scan_mma_max_queries() {
 bool scan_mma_available() { return true; }
 
 cudaError_t launch_scan_mma(const ScanParams& p, const __nv_bfloat16* q_bf16, int32_t n_q_padded,
-                            int mode, int32_t* flags, int sm_count, cudaStream_t stream) {
+                            int mode, int32_t* flags, int sm_count, cudaStream_t stream, int split) {
   const int n_qchunks = (p.nq + kMaxQ - 1) / kMaxQ;
   if (p.nq < 1 || n_qchunks > kMaxQChunks) return cudaErrorInvalidValue;
+  if (split != 1 && split != 3) return cudaErrorInvalidValue;
+  if (split == 3 && p.nq > kSplitMaxQ) return cudaErrorInvalidValue;
   if (p.n_rows > 0x7fffffffll - kBlockM) return cudaErrorInvalidValue;   // TMA coordinates are int32
   MmaCfg cfg;
   cfg.n_umma = n_qchunks > 1 ? kMaxQ : (p.nq + 15) / 16 * 16;   // multi-chunk launches: full-width tiles (padded columns never pass)
@@ -333,15 +364,18 @@ cudaError_t launch_scan_mma(const ScanParams& p, const __nv_bfloat16* q_bf16, in
   while (cols < 2 * cfg.n_umma) cols <<= 1;
   cfg.tmem_cols = cols;
   cfg.acc_stride = cols / 2;
+  cfg.split = split;
+  cfg.g_plane_rows = p.n_rows;
+  cfg.q_plane_rows = n_q_padded;
   cfg.debug_skip_epilogue = getenv("MMRS_K2_DEBUG_SKIP_EPI") ? atoi(getenv("MMRS_K2_DEBUG_SKIP_EPI")) : 0;   // 1: no epilogue, 2: nothing passes
-  const size_t stage_bytes = static_cast<size_t>(kABytes) + static_cast<size_t>(cfg.n_umma) * kBlockK * 2;
+  const size_t stage_bytes = split * (static_cast<size_t>(kABytes) + static_cast<size_t>(cfg.n_umma) * kBlockK * 2);
   // Up to 128 queries the CTA is sized so that TWO fit on an SM (<= 113 KB of shared memory, 80
   // registers x 384 threads, <= 256 TMEM columns each): the scans of two searches in flight on
   // different streams then share the HBM stream instead of queueing behind each other, and the
   // short seed/mid scans of one search hide under the long last-phase scan of the other.
   int small_max = 128;   // 33..128 queries: 3-4 ring stages per CTA, two CTAs per SM
   if (const char* e = getenv("MMRS_K2_SMALL_MAX")) small_max = atoi(e);
-  const bool small = cfg.n_umma <= small_max && getenv("MMRS_K2_BIG_SMEM") == nullptr;
+  const bool small = split == 1 && cfg.n_umma <= small_max && getenv("MMRS_K2_BIG_SMEM") == nullptr;
   const size_t budget = (small ? 113 * 1024 : 227 * 1024) - sizeof(MmaShared) - 1024 - (small ? 1024 : 0);
   int stages = static_cast<int>(budget / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
@@ -350,10 +384,11 @@ cudaError_t launch_scan_mma(const ScanParams& p, const __nv_bfloat16* q_bf16, in
   const size_t smem = 1024 + stage_bytes * stages + sizeof(MmaShared);
 
   CUtensorMap map_g, map_q;
-  if (!make_map(&map_g, p.gallery, static_cast<uint64_t>(p.n_rows), static_cast<uint64_t>(p.dim),
+  if (static_cast<int64_t>(split) * p.n_rows > 0x7fffffffll - kBlockM) return cudaErrorInvalidValue;
+  if (!make_map(&map_g, p.gallery, static_cast<uint64_t>(split) * p.n_rows, static_cast<uint64_t>(p.dim),
                 static_cast<uint64_t>(p.ld), kBlockM))
     return cudaErrorNotSupported;
-  if (!make_map(&map_q, q_bf16, static_cast<uint64_t>(n_q_padded), static_cast<uint64_t>(p.ldq),
+  if (!make_map(&map_q, q_bf16, static_cast<uint64_t>(split) * n_q_padded, static_cast<uint64_t>(p.ldq),
                 static_cast<uint64_t>(p.ldq), static_cast<uint32_t>(cfg.n_umma)))
     return cudaErrorNotSupported;
 

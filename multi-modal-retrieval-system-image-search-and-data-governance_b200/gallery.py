@@ -65,6 +65,7 @@ class DeviceGallery:
         self.data = data
         self.padded_dim = dp
         self._workspaces: dict = {}
+        self._split = None
 
     # -- C-ABI views ---------------------------------------------------------------------------
     @property
@@ -103,6 +104,21 @@ class DeviceGallery:
     def aligned_ptr(buf: torch.Tensor) -> int:
         p = buf.data_ptr()
         return (p + 255) // 256 * 256
+
+    def split3(self) -> torch.Tensor:
+        """fp32 mode only: the gallery as three bf16 planes [3, N, Dp] with x == hi + mid + lo, built
+        once on first use (mmrs_split_bf16x3).  Larger fp32 batches are searched from these planes on
+        the tensor cores (six bf16 MMAs per tile, fp32-grade scores) instead of K1's CUDA-core passes."""
+        if self.mode != "fp32":
+            raise ValueError("split planes exist for fp32 galleries only")
+        if self._split is None:
+            planes = torch.empty((3, self.n_rows, self.padded_dim), dtype=torch.bfloat16, device=self.device)
+            with torch.cuda.device(self.device):
+                _cabi.check(_cabi.lib.mmrs_split_bf16x3(self.data.data_ptr(), self.n_rows, self.padded_dim,
+                                                        self.data.stride(0), planes.data_ptr(), self.padded_dim,
+                                                        int(torch.cuda.current_stream(self.device).cuda_stream)))
+            self._split = planes
+        return self._split
 
     def lookup_paths(self, indices):
         """Relative paths (the keys of the reference's feature pickle, search_image.py:157) of the

@@ -59,6 +59,17 @@ def _prep_queries(queries, gal: DeviceGallery):
     return q, not q.is_cuda
 
 
+FP32_TC_MIN_QUERIES = 9     # fp32 galleries: K1 (CUDA cores) up to 8 queries, bf16x3 tensor-core path beyond
+
+
+def _operand(gal: DeviceGallery, nq: int, path: str):
+    """(pointer, row stride, dtype code) of the gallery operand the library should scan."""
+    if gal.mode == "fp32" and path != "gemv" and (nq >= FP32_TC_MIN_QUERIES or path == "mma"):
+        planes = gal.split3()
+        return planes.data_ptr(), planes.stride(1), _cabi.DTYPE_BF16X3
+    return gal.data.data_ptr(), gal.data.stride(0), gal.dtype_code
+
+
 class PendingSearch:
     """Handle of an asynchronous search (`search_topk(..., sync=False)`): `values` / `indices` are
     filled once the work enqueued on the stream has run; `wait()` blocks until then, checks the
@@ -120,7 +131,8 @@ def search_topk(queries, gallery: GalleryLike, k: int, *, normalize_queries: boo
         indices = torch.empty((nq, k), dtype=torch.int64, device=dev)
     if nq == 0:
         return (values, indices) if sync else PendingSearch(values, indices, None, None, None)
-    args = (gal.data.data_ptr(), gal.n_rows, gal.padded_dim, gal.data.stride(0), gal.dtype_code,
+    g_ptr, g_ld, g_dtype = _operand(gal, nq, path)
+    args = (g_ptr, gal.n_rows, gal.padded_dim, g_ld, g_dtype,
             q.data_ptr(), nq, q.stride(0), k, int(bool(normalize_queries)), float(scale),
             gal.row_offset, _cabi.PATHS[path], values.data_ptr(), indices.data_ptr(), ws_ptr, ws_bytes)
     if sync:
@@ -154,8 +166,9 @@ def full_scores(queries, gallery: GalleryLike, *, normalize_queries: bool = True
         if nq > 0:
             ws_bytes = lib.mmrs_full_scores_workspace_bytes(gal.n_rows, gal.padded_dim, gal.dtype_code, nq)
             ws = gal.workspace(("scores", nq), ws_bytes)
-            _cabi.check(lib.mmrs_full_scores(gal.data.data_ptr(), gal.n_rows, gal.padded_dim,
-                                             gal.data.stride(0), gal.dtype_code, q.data_ptr(), nq,
+            g_ptr, g_ld, g_dtype = _operand(gal, nq, path)
+            _cabi.check(lib.mmrs_full_scores(g_ptr, gal.n_rows, gal.padded_dim,
+                                             g_ld, g_dtype, q.data_ptr(), nq,
                                              q.stride(0), int(bool(normalize_queries)), float(scale),
                                              _cabi.PATHS[path], out.data_ptr(), out.stride(0),
                                              DeviceGallery.aligned_ptr(ws), ws_bytes,

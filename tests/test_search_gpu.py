@@ -369,3 +369,31 @@ def test_device_resident_threshold_sweep(mm, oracle):
         assert (best_f1, best_thr) == (want[0], want[1])
         # and against the recorded output of the reference's own function (scores differ by <= 1e-3)
         assert abs(best_f1 - float(gold[f"{name}_best_f1"])) < 0.02
+
+
+# ---- fp32 mode on the tensor cores (bf16 x 3 split, six MMAs per tile) ----------------------------------
+@pytest.mark.parametrize("n,d,nq,k", [(4096, 512, 9, 100), (20_000, 768, 48, 10), (70_001, 72, 49, 100),
+                                      (300_000, 128, 100, 10), (16_385, 520, 130, 1)])
+def test_fp32_tensor_core_path_matches_oracle(mm, oracle, n, d, nq, k):
+    g = oracle.synthetic_gallery(n, d, seed=(n * 7 + d) % 83, dtype=torch.float32)
+    q = oracle.synthetic_queries(nq, d, seed=nq + 1)
+    gal = mm.DeviceGallery(g, mode="fp32")
+    want_v, want_i = oracle.search_topk(q, g, k, mode="fp32")
+    v, i = mm.search_topk(q, gal, k)                       # >= 9 queries: split planes + tcgen05
+    assert gal._split is not None
+    np.testing.assert_allclose(v.numpy(), want_v.numpy(), atol=1e-5, rtol=0)
+    n_bad = explain_index_mismatches(i.numpy(), want_i.numpy(), want_v.numpy(), 1e-5)
+    assert n_bad <= max(1, i.numel() // 200)
+    # the CUDA-core exact path agrees to fp32 rounding
+    v1, i1 = mm.search_topk(q[:8], gal, k, path="gemv")
+    np.testing.assert_allclose(v1.numpy(), v[:8].numpy(), atol=2e-6, rtol=0)
+
+
+def test_fp32_tensor_core_c1_shape_and_full_scores(mm, oracle):
+    gen = torch.Generator().manual_seed(1)
+    base = torch.randn(512, generator=gen)
+    g = oracle.l2_normalize(base + 0.1 * torch.randn(10_000, 512, generator=gen))   # C1: collinear features
+    q = base + 0.1 * torch.randn(100, 512, generator=gen)
+    check_fp32(mm, oracle, g, q, 10, max_swapped=0.03)
+    s = mm.full_scores(q, mm.DeviceGallery(g, mode="fp32"), scale=100.0)
+    np.testing.assert_allclose(s.numpy(), oracle.full_scores(q, g, scale=100.0).numpy(), atol=1e-3, rtol=0)
