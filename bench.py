@@ -418,6 +418,7 @@ def main():
         }
         if sweep:
             line["sweep"] = sweep
+            line["sweep_mode"] = "one blocking call at a time (no batches in flight), device-resident queries"
         if timeline:
             line["kernel_timeline_ms"] = timeline
         print(json.dumps(line), flush=True)
