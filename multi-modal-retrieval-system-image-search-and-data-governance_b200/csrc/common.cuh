@@ -156,7 +156,6 @@ cudaError_t launch_scan_gemv(const ScanParams& p, int32_t dtype, int mode, int s
                              cudaStream_t stream);
 cudaError_t launch_select(const SelectParams& p, int32_t n_queries, cudaStream_t stream);
 cudaError_t launch_fill_u32(uint32_t* p, uint32_t v, int64_t n, cudaStream_t stream);
-cudaError_t launch_fill_f32(float* p, float v, int64_t n, cudaStream_t stream);
 cudaError_t launch_pack_keys(const float* values, const int64_t* indices, int32_t n_lists,
                              int32_t n_queries, int32_t k_in, uint64_t* cand, int32_t cap,
                              cudaStream_t stream);

@@ -308,10 +308,5 @@ cudaError_t launch_fill_u32(uint32_t* p, uint32_t v, int64_t n, cudaStream_t str
   fill_kernel<uint32_t><<<static_cast<int>((n + 255) / 256), 256, 0, stream>>>(p, v, n);
   return cudaGetLastError();
 }
-cudaError_t launch_fill_f32(float* p, float v, int64_t n, cudaStream_t stream) {
-  if (n <= 0) return cudaSuccess;
-  fill_kernel<float><<<static_cast<int>((n + 255) / 256), 256, 0, stream>>>(p, v, n);
-  return cudaGetLastError();
-}
 
 }  // namespace mmrs

@@ -7,8 +7,8 @@
 // every pair i < j of an upper-triangular 128x128 block schedule and appends the hits.
 //
 // Exact mode: fp32 FFMA, k ascending, one accumulator per pair -- the pair set does not depend
-// on tile shape or launch geometry.  (The tensor-core prefilter + exact recheck variant lives in
-// selfjoin_mma.cu once K2's pipeline is proven.)
+// on tile shape or launch geometry.  selfjoin_mma.cu is the tensor-core prefilter whose survivors are
+// re-scored with exactly this arithmetic; this kernel serves small inputs and as its cross-check.
 #include "common.cuh"
 
 namespace mmrs {
