@@ -326,6 +326,35 @@ def best_threshold_on_device(scores: torch.Tensor, targets, label, n_points: int
     return best[0], best[1], best[2], best[3], thresholds, f1s
 
 
+def evaluate_thresholds(similarities, thresholds, positive_class, negative_class):
+    """Drop-in for `evaluate_thresholds` of CLIP/lab3.py:39-65 (also CLIP-Chinese/lab_chinese.py,
+    CLIP/union_dataset.py:46): `similarities` is the list of {"similarity", "true_label", ...} dicts the
+    lab scripts build, only items of the two named classes count; returns one dict per threshold with
+    threshold / precision / recall / f1 / TP / FP / TN / FN (0 where a denominator is 0).  The
+    O(T * N) generator sums of :47-48 (1001 thresholds) run as one GPU histogram pass."""
+    rel = [it for it in similarities if it["true_label"] in [positive_class, negative_class]]
+    sim64 = np.array([it["similarity"] for it in rel], dtype=np.float64)
+    sim32 = sim64.astype(np.float32)
+    if not np.array_equal(sim32.astype(np.float64), sim64):
+        raise ValueError("similarities must be fp32-representable (they are float(fp32 cosine) in the lab scripts)")
+    is_pos = np.array([it["true_label"] == positive_class for it in rel], dtype=bool)
+    total_pos, total_neg = int(is_pos.sum()), int((~is_pos).sum())
+    thr = np.asarray(thresholds, dtype=np.float64).reshape(-1)
+    order = np.argsort(thr, kind="stable")
+    tp_s, fp_s = threshold_sweep_counts(sim32[is_pos], sim32[~is_pos], thr[order])
+    tp = np.empty_like(tp_s); fp = np.empty_like(fp_s)
+    tp[order], fp[order] = tp_s, fp_s
+    results = []
+    for threshold, TP, FP in zip(thresholds, tp.tolist(), fp.tolist()):
+        FN, TN = total_pos - TP, total_neg - FP
+        precision = TP / (TP + FP) if (TP + FP) > 0 else 0
+        recall = TP / (TP + FN) if (TP + FN) > 0 else 0
+        f1 = 2 * precision * recall / (precision + recall) if (precision + recall) > 0 else 0
+        results.append({"threshold": threshold, "precision": precision, "recall": recall, "f1": f1,
+                        "TP": TP, "FP": FP, "TN": TN, "FN": FN})
+    return results
+
+
 def eval_threshold(pos_res, neg_res, threshold):
     """Drop-in for code/search_image.py:39-56 -> (f1_score, precision, recall)."""
     tp, fp = threshold_sweep_counts(pos_res, neg_res, [threshold])

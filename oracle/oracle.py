@@ -181,6 +181,27 @@ def find_thresholds(pos_res, neg_res, n_points: int = 200):
 
 
 # --------------------------------------------------------------------------------------------
+# evaluate_thresholds: CLIP/lab3.py:39-65 (same in CLIP-Chinese/lab_chinese.py, CLIP/union_dataset.py:46)
+# --------------------------------------------------------------------------------------------
+def lab_evaluate_thresholds(similarities, thresholds, positive_class, negative_class):
+    rel = [it for it in similarities if it["true_label"] in [positive_class, negative_class]]
+    sim = np.array([it["similarity"] for it in rel], dtype=np.float64)
+    is_pos = np.array([it["true_label"] == positive_class for it in rel], dtype=bool)
+    total_pos, total_neg = int(is_pos.sum()), int((~is_pos).sum())
+    results = []
+    for threshold in thresholds:
+        TP = int(np.sum((sim >= threshold) & is_pos))
+        FP = int(np.sum((sim >= threshold) & ~is_pos))
+        FN, TN = total_pos - TP, total_neg - FP
+        precision = TP / (TP + FP) if (TP + FP) > 0 else 0
+        recall = TP / (TP + FN) if (TP + FN) > 0 else 0
+        f1 = 2 * precision * recall / (precision + recall) if (precision + recall) > 0 else 0
+        results.append({"threshold": threshold, "precision": precision, "recall": recall, "f1": f1,
+                        "TP": TP, "FP": FP, "TN": TN, "FN": FN})
+    return results
+
+
+# --------------------------------------------------------------------------------------------
 # near-duplicate self-join (BASELINE.json north_star):
 #   triu((G @ G.T) >= tau, 1).nonzero()   -- row-major nonzero == lexicographic (i, j)
 # --------------------------------------------------------------------------------------------

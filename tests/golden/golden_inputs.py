@@ -69,3 +69,17 @@ def dedup_image_set(root: str):
     with open(os.path.join(del_dir, "broken.png"), "wb") as f:    # unreadable: hash None -> kept (:67-69)
         f.write(b"not an image")
     return ref_dir, del_dir
+
+
+def lab3_inputs():
+    """(similarities list-of-dicts, thresholds, positive_class, negative_class) as CLIP/lab3.py:108-122 builds
+    them: float(fp32 cosine), string labels, a 1001-point linspace; a third class is present and must be ignored."""
+    g = torch.Generator().manual_seed(21)
+    n = 3000
+    labels = ["dog", "others", "cat"]
+    lab = torch.randint(0, 3, (n,), generator=g)
+    sim = (0.22 + 0.05 * torch.randn(n, generator=g) + 0.06 * (lab == 0)).to(torch.float32)
+    similarities = [{"similarity": float(s), "true_label": labels[int(l)], "file_path": f"{i}.jpg"}
+                    for i, (s, l) in enumerate(zip(sim, lab))]
+    thresholds = np.linspace(0.0, 0.5, 1001)
+    return similarities, thresholds, "dog", "others"

@@ -9,6 +9,7 @@ their inputs' seeds and their OUTPUTS are stored (tests/golden/*.npz, *.json).
 
   code/search_image.py   get_similarity (:105-117), eval_threshold (:39-56), find_thresholds (:58-103)
   code/utils.py          cls_acc (:15-39)  -> the only topk in the repo (:17)
+  CLIP/lab3.py           evaluate_thresholds (:39-65)
   tool/find_repeated.py  calculate_image_hash (:6-19), get_all_images (:21-33),
                          find_and_remove_duplicate_images (:35-71)
 
@@ -30,7 +31,7 @@ import torch
 
 HERE = Path(__file__).resolve().parent
 sys.path.insert(0, str(HERE))
-from golden_inputs import (dedup_image_set, similarity_inputs, topk_inputs)  # noqa: E402
+from golden_inputs import (dedup_image_set, lab3_inputs, similarity_inputs, topk_inputs)  # noqa: E402
 
 
 def extract_functions(path: Path, names: list[str], namespace: dict) -> dict:
@@ -77,6 +78,14 @@ def main(ref_root: str) -> None:
             out2[f"{name}_topk{k}_values"] = v.numpy()
             out2[f"{name}_topk{k}_indices"] = i.numpy()
     np.savez(HERE / "utils_topk_golden.npz", **out2)
+
+    # ---- CLIP/lab3.py evaluate_thresholds (:39-65) -----------------------------------------------
+    ns4 = {}
+    extract_functions(ref / "CLIP" / "lab3.py", ["evaluate_thresholds"], ns4)
+    sims, thresholds, pos_cls, neg_cls = lab3_inputs()
+    res = ns4["evaluate_thresholds"](sims, thresholds, pos_cls, neg_cls)
+    keys = ["threshold", "precision", "recall", "f1", "TP", "FP", "TN", "FN"]
+    np.savez(HERE / "lab3_golden.npz", **{k: np.array([r[k] for r in res], dtype=np.float64) for k in keys})
 
     # ---- tool/find_repeated.py --------------------------------------------------------------
     import hashlib

@@ -123,3 +123,12 @@ def test_greedy_keep_first(oracle):
     assert reps == [0, 2] and dups == [(1, 0)]
     reps, dups = oracle.greedy_keep_first(4, [(0, 3), (1, 3)], [1, 0, 3, 2])
     assert reps == [1, 0, 2] and dups == [(3, 1)]
+
+
+def test_lab3_evaluate_thresholds_matches_reference(oracle):
+    from golden_inputs import lab3_inputs
+    g = np.load(GOLDEN / "lab3_golden.npz")
+    sims, thresholds, pos_cls, neg_cls = lab3_inputs()
+    res = oracle.lab_evaluate_thresholds(sims, thresholds, pos_cls, neg_cls)
+    for key in ("threshold", "precision", "recall", "f1", "TP", "FP", "TN", "FN"):
+        np.testing.assert_array_equal(np.array([r[key] for r in res], dtype=np.float64), g[key])

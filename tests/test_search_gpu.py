@@ -397,3 +397,16 @@ def test_fp32_tensor_core_c1_shape_and_full_scores(mm, oracle):
     check_fp32(mm, oracle, g, q, 10, max_swapped=0.03)
     s = mm.full_scores(q, mm.DeviceGallery(g, mode="fp32"), scale=100.0)
     np.testing.assert_allclose(s.numpy(), oracle.full_scores(q, g, scale=100.0).numpy(), atol=1e-3, rtol=0)
+
+
+def test_lab3_evaluate_thresholds_golden(mm):
+    """f3: the lab scripts' 1001-point sweep through the GPU histogram equals the reference's own output."""
+    from golden_inputs import lab3_inputs
+    g = np.load(GOLDEN / "lab3_golden.npz")
+    sims, thresholds, pos_cls, neg_cls = lab3_inputs()
+    res = mm.evaluate_thresholds(sims, thresholds, pos_cls, neg_cls)
+    assert len(res) == 1001 and set(res[0]) == {"threshold", "precision", "recall", "f1", "TP", "FP", "TN", "FN"}
+    for key in ("threshold", "precision", "recall", "f1", "TP", "FP", "TN", "FN"):
+        np.testing.assert_array_equal(np.array([r[key] for r in res], dtype=np.float64), g[key])
+    best = max(res, key=lambda x: x["f1"])              # lab3.py:123
+    assert best["f1"] == g["f1"].max()
