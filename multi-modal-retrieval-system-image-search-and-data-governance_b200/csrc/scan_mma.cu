@@ -17,6 +17,16 @@
 // The accumulator is double buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
 // Roofline: HBM-bound (N*D*2 bytes per pass) up to Q ~ 200, tensor-bound beyond
 // (SURVEY.md section 8d).
+//
+// PAIR mode (more than 128 queries): the grid is launched as clusters of two CTAs (one TPC) that
+// run ONE tcgen05.mma.cta_group::2 of M = 256: each CTA stages its own gallery tile (A, 128 rows)
+// and HALF of the query chunk (B); CTA 0's MMA warp issues for both, each CTA's accumulator
+// (its 128 rows x all queries of the chunk) lands in its own TMEM and is read out by its own
+// epilogue warps.  With one SM per MMA the tensor pipe idles a third of the time waiting for its
+// shared-memory operands (A + B = 12 KB per 128 clocks; ncu: 66 % duty with the ring always full,
+// profiles/r01_k2_c5like_summary.txt); the pair halves the B traffic per SM.  Work units of a
+// pair are (tile pair, query chunk) in chunk-minor order, so the chunks of one tile pair are
+// scanned by neighbouring pairs at the same time and share the tile through L2.
 #include <stdlib.h>
 
 #include "tcgen05_utils.cuh"
@@ -35,17 +45,19 @@ constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KiB
 constexpr int kMaxStages = 8;
 constexpr uint32_t kStash = 4;            // parked candidates per epilogue thread before a flush
 
-struct MmaShared {
+template <int CHUNKS>   // query chunks whose thresholds a CTA keeps: 1, or kMaxQChunks in pair mode
+struct MmaSharedT {
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
   volatile uint32_t abort;
-  alignas(16) float thr[kMaxQ];       // exact bound on the scaled score
-  alignas(16) float thr_raw[kMaxQ];   // conservative bound on the RAW accumulator (thr / scale, nudged down)
+  alignas(16) float thr[kMaxQ * CHUNKS];       // exact bound on the scaled score
+  alignas(16) float thr_raw[kMaxQ * CHUNKS];   // conservative bound on the RAW accumulator (thr / scale, nudged down)
   alignas(16) uint2 stash[kMaxEpiWarps][kStash * 32];  // per epilogue thread: parked (column, score) pairs
 };
+using MmaShared = MmaSharedT<1>;
 
 struct MmaCfg {
   int32_t n_umma;        // UMMA N: queries of this pass rounded up to 16
@@ -57,30 +69,32 @@ struct MmaCfg {
   int64_t g_plane_rows;  // split == 3: rows between two planes of the gallery (= n_rows)
   int32_t q_plane_rows;  // split == 3: rows between two planes of the prepared queries
   int32_t debug_skip_epilogue;   // measurement aid (MMRS_K2_DEBUG_SKIP_EPI=1): results are garbage
+  int32_t n_qchunks;     // pair mode: query chunks of kMaxQ in this launch (they are work units, not gridDim.y)
 };
 
+// The tiles of a phase are t = j * inc, j in [0, n_sel), except those with t % exc == 0, i.e.
+// j % R == 0 with R = exc / inc (strides are powers of two, plan.h).  The v-th tile that IS visited:
+__device__ __forceinline__ int valid_to_j(int v, int R) { return R ? (v / (R - 1)) * R + v % (R - 1) + 1 : v; }
 
-template <int MODE, int EPI_WARPS>
+
+template <int MODE, int EPI_WARPS, bool PAIR>
 __global__ void __launch_bounds__((kCtrlWarps + EPI_WARPS) * 32, EPI_WARPS == 8 ? 2 : 1)
 scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_q,
                 const ScanParams p, const MmaCfg cfg, int32_t* flags) {
+  using Shared = MmaSharedT<PAIR ? kMaxQChunks : 1>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // dynamic smem: [stages x (A 16 KiB | B n_umma*128 B)] then MmaShared; the ring must be
-  // 1024-byte aligned for the 128-byte swizzle
+  // dynamic smem: [stages x (A 16 KiB | B rows*128 B)] then Shared; the ring must be
+  // 1024-byte aligned for the 128-byte swizzle.  B rows: n_umma, in pair mode n_umma / 2.
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t b_bytes = static_cast<uint32_t>(cfg.n_umma) * kBlockK * 2;
+  const int b_rows = PAIR ? cfg.n_umma / 2 : cfg.n_umma;
+  const uint32_t b_bytes = static_cast<uint32_t>(b_rows) * kBlockK * 2;
   // split == 3 (fp32 emulation): a stage holds the hi/mid/lo planes of both operands,
   // [A_hi | A_mid | A_lo | B_hi | B_mid | B_lo]
   const uint32_t a_all = static_cast<uint32_t>(cfg.split) * kABytes;
   const uint32_t stage_bytes = static_cast<uint32_t>(cfg.split) * (kABytes + b_bytes);
-  MmaShared* sh = reinterpret_cast<MmaShared*>(ring + static_cast<size_t>(cfg.stages) * stage_bytes);
+  Shared* sh = reinterpret_cast<Shared*>(ring + static_cast<size_t>(cfg.stages) * stage_bytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // gridDim.y query chunks share every gallery tile: CTA (x, y) scans the tiles of slot x for the
-  // kMaxQ queries of chunk y.  The chunks' CTAs walk the same tile sequence at the same pace, so the
-  // second one finds the tile in L2 and the HBM stream per query is divided by gridDim.y.
-  const int q0 = p.q0 + static_cast<int>(blockIdx.y) * kMaxQ;
-  const int nq = min(p.nq - static_cast<int>(blockIdx.y) * kMaxQ, kMaxQ);
   // Warp roles.  The epilogue warps take the LOW warp ids and the three control warps the highest:
   // the warp schedulers favour the higher warp id among ready warps (B300_MICROARCH.md, arbiter:
   // hi-wid-first), so the single threads that issue TMA and tcgen05.mma cannot be queued behind
@@ -89,9 +103,37 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
   // order that cannot hurt.)  TMEM lane quarters go by warp id % 4, unaffected.
   constexpr int kTmaWarp = EPI_WARPS, kMmaWarp = EPI_WARPS + 1, kAllocWarp = EPI_WARPS + 2;
 
+  // ---- work units ---------------------------------------------------------------------------
+  // A unit is one accumulator tile: (gallery tile, query chunk).  Without pairs, CTA (x, y) walks
+  // j = x, x + gridDim.x, ... (skipping the tiles an earlier phase covered) for the kMaxQ queries of
+  // chunk y: the chunks' CTAs walk the same tile sequence at the same pace, so all but the first
+  // find the tile in L2 and the HBM stream per query is divided by gridDim.y.  In pair mode the
+  // pair walks units u = pair, pair + n_pairs, ...: u -> (tile pair u / n_qchunks, chunk
+  // u % n_qchunks) over the VISITED tiles only; CTA `rank` of the pair takes tile 2 * (tile pair) + rank.
+  const int inc = p.sched.tile_inc, exc = p.sched.tile_exc;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int R = PAIR && exc ? exc / inc : 0;
+  const int n_valid = R == 1 ? 0 : (R ? p.sched.n_sel - (p.sched.n_sel + R - 1) / R : p.sched.n_sel);
+  const int n_ch = PAIR ? cfg.n_qchunks : 1;
+  const int u_begin = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int u_step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int n_units = PAIR ? (n_valid + 1) / 2 * n_ch : p.sched.n_sel;
+  struct Unit { int j, chunk; bool valid, skip; };
+  auto unit_of = [&](int u) -> Unit {
+    if constexpr (PAIR) {
+      const int tp = u / n_ch;
+      const int v = 2 * tp + static_cast<int>(rank);
+      const bool valid = v < n_valid;     // an odd tile count leaves the last pair half empty:
+      return Unit{valid_to_j(valid ? v : 2 * tp, R), u - tp * n_ch, valid, false};   // that CTA repeats its partner's tile, unread
+    } else {
+      return Unit{u, static_cast<int>(blockIdx.y), true, exc != 0 && ((u * inc) % exc) == 0};
+    }
+  };
+
   if (threadIdx.x == 0) {
     for (int s = 0; s < cfg.stages; ++s) { mbar_init(&sh->full[s], 1); mbar_init(&sh->empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&sh->tmem_full[a], 1); mbar_init(&sh->tmem_empty[a], EPI_WARPS); }
+    // pair mode: the leader's tmem_empty collects the epilogue warps of both CTAs
+    for (int a = 0; a < 2; ++a) { mbar_init(&sh->tmem_full[a], 1); mbar_init(&sh->tmem_empty[a], PAIR ? 2 * EPI_WARPS : EPI_WARPS); }
     sh->abort = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_g)) : "memory");
@@ -99,10 +141,17 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
   }
   pdl_launch_dependents();
   if (warp == kAllocWarp) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)),
-                 "r"(static_cast<uint32_t>(cfg.tmem_cols))
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (PAIR) {   // both CTAs of the pair, same warp id, same destination offset
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)),
+                   "r"(static_cast<uint32_t>(cfg.tmem_cols))
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)),
+                   "r"(static_cast<uint32_t>(cfg.tmem_cols))
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   pdl_wait();   // everything above overlaps the predecessor; its results are read from here on
   // The hot loop compares the RAW accumulator with thr / scale (no multiply per score); that bound
@@ -110,94 +159,126 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
   // exact test `scale * acc >= thr` before parking a candidate.  Non-positive scales keep the
   // multiply (raw_ok = false).
   const bool raw_ok = p.scale > 0.f;
-  for (int c = threadIdx.x; c < kMaxQ; c += (kCtrlWarps + EPI_WARPS) * 32) {
-    float t = __int_as_float(0x7f800000);  // +inf: padded columns never pass the filter
-    if (MODE == kModeFilter && c < nq && cfg.debug_skip_epilogue != 2) t = p.thr[q0 + c];
-    sh->thr[c] = t;
-    float tr = t;
-    if (raw_ok && isfinite(t)) {
-      tr = t / p.scale;
-      tr = tr - fabsf(tr) * 4.8e-7f - 1e-37f;
+  {
+    const int first_q = PAIR ? p.q0 : p.q0 + static_cast<int>(blockIdx.y) * kMaxQ;
+    const int n_q = PAIR ? p.nq : min(p.nq - static_cast<int>(blockIdx.y) * kMaxQ, kMaxQ);
+    for (int c = threadIdx.x; c < kMaxQ * (PAIR ? kMaxQChunks : 1); c += (kCtrlWarps + EPI_WARPS) * 32) {
+      float t = __int_as_float(0x7f800000);  // +inf: padded columns never pass the filter
+      if (MODE == kModeFilter && c < n_q && cfg.debug_skip_epilogue != 2) t = p.thr[first_q + c];
+      sh->thr[c] = t;
+      float tr = t;
+      if (raw_ok && isfinite(t)) {
+        tr = t / p.scale;
+        tr = tr - fabsf(tr) * 4.8e-7f - 1e-37f;
+      }
+      sh->thr_raw[c] = tr;
     }
-    sh->thr_raw[c] = tr;
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) {
+    __syncwarp();
+    cluster_sync_all();   // the peer's barriers are initialised before anything is signalled across
+  } else {
+    __syncthreads();
+  }
   tcgen05_fence_after();
   const uint32_t tmem_base = sh->tmem_base;
-
-  const int n_sel = p.sched.n_sel, inc = p.sched.tile_inc, exc = p.sched.tile_exc;
 
   if (warp == kTmaWarp) {
     // ===== TMA producer =====
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       bool ok = true;
-      for (int j = blockIdx.x; j < n_sel && ok; j += gridDim.x) {
-        const int t = j * inc;
-        if (exc != 0 && (t % exc) == 0) continue;
-        const int32_t row0 = t * kBlockM;
+      for (int u = u_begin; u < n_units && ok; u += u_step) {
+        const Unit un = unit_of(u);
+        if (un.skip) continue;
+        const int32_t row0 = un.j * inc * kBlockM;
+        const int32_t qrow0 = p.q0 + un.chunk * kMaxQ + static_cast<int>(rank) * b_rows;
         for (int kb = 0; kb < cfg.k_blocks; ++kb) {
           if (!mbar_wait(&sh->empty[stage], phase ^ 1, &sh->abort, flags)) { ok = false; break; }
           uint8_t* a_dst = ring + static_cast<size_t>(stage) * stage_bytes;
-          mbar_expect_tx(&sh->full[stage], stage_bytes);
-          for (int pl = 0; pl < cfg.split; ++pl) {
-            tma_load_2d(a_dst + pl * kABytes, &map_g, &sh->full[stage], kb * kBlockK,
-                        static_cast<int32_t>(pl * cfg.g_plane_rows) + row0, kEvictFirst);
-            tma_load_2d(a_dst + a_all + pl * b_bytes, &map_q, &sh->full[stage], kb * kBlockK,
-                        pl * cfg.q_plane_rows + q0, kEvictLast);
+          if constexpr (PAIR) {
+            // both halves of the stage are credited to the LEADER's barrier, which its MMA warp waits on
+            const uint32_t full_leader = mapa_u32(smem_u32(&sh->full[stage]), 0);
+            if (rank == 0) mbar_expect_tx(&sh->full[stage], 2 * stage_bytes);
+            tma_load_2d_pair(a_dst, &map_g, full_leader, kb * kBlockK, row0, kEvictFirst);
+            tma_load_2d_pair(a_dst + kABytes, &map_q, full_leader, kb * kBlockK, qrow0, kEvictLast);
+          } else {
+            mbar_expect_tx(&sh->full[stage], stage_bytes);
+            for (int pl = 0; pl < cfg.split; ++pl) {
+              tma_load_2d(a_dst + pl * kABytes, &map_g, &sh->full[stage], kb * kBlockK,
+                          static_cast<int32_t>(pl * cfg.g_plane_rows) + row0, kEvictFirst);
+              tma_load_2d(a_dst + a_all + pl * b_bytes, &map_q, &sh->full[stage], kb * kBlockK,
+                          pl * cfg.q_plane_rows + qrow0, kEvictLast);
+            }
           }
           if (++stage == static_cast<uint32_t>(cfg.stages)) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == kMmaWarp) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(static_cast<uint32_t>(cfg.n_umma));
+    // ===== MMA issuer (pair mode: the leader CTA issues for both) =====
+    // The WHOLE warp walks the loop and one elected lane issues: with the loop inside `if (lane == 0)`
+    // every descriptor lived in vector registers and each tcgen05.mma cost an ELECT + five R2UR +
+    // predicate shuffling -- ~125 instructions and 778 clocks per k-block against the 512 clocks its
+    // four MMAs keep the tensor pipe busy (ncu: ring always full, pipe 66 % active,
+    // profiles/r01_k2_c5like_summary.txt).  Warp-uniform code keeps them in uniform registers.
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc(static_cast<uint32_t>(cfg.n_umma), PAIR ? 256u : 128u);
+      const uint32_t ring_addr = smem_u32(ring);
       uint32_t stage = 0, phase = 0, it = 0;
       bool ok = true;
-      for (int j = blockIdx.x; j < n_sel && ok; j += gridDim.x) {
-        const int t = j * inc;
-        if (exc != 0 && (t % exc) == 0) continue;
+      for (int u = u_begin; u < n_units && ok; u += u_step) {
+        if (unit_of(u).skip) continue;
         const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-        if (!mbar_wait(&sh->tmem_empty[as], aphase ^ 1, &sh->abort, flags)) break;
+        if (!__all_sync(0xffffffffu, mbar_wait(&sh->tmem_empty[as], aphase ^ 1, &sh->abort, flags))) break;
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + as * static_cast<uint32_t>(cfg.acc_stride);
         for (int kb = 0; kb < cfg.k_blocks; ++kb) {
-          if (!mbar_wait(&sh->full[stage], phase, &sh->abort, flags)) { ok = false; break; }
+          if (!__all_sync(0xffffffffu, mbar_wait(&sh->full[stage], phase, &sh->abort, flags))) { ok = false; break; }
           tcgen05_fence_after();
-          const uint32_t a_addr = smem_u32(ring + static_cast<size_t>(stage) * stage_bytes);
-          if (cfg.split == 1) {
-            const uint64_t adesc = make_sw128_desc(a_addr);
-            const uint64_t bdesc = make_sw128_desc(a_addr + kABytes);
+          const uint32_t a_addr = ring_addr + stage * stage_bytes;
+          if (elect_one()) {
+            if (PAIR || cfg.split == 1) {
+              const uint64_t adesc = make_sw128_desc(a_addr);
+              const uint64_t bdesc = make_sw128_desc(a_addr + kABytes);
 #pragma unroll
-            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-              // advancing 16 bf16 along K inside the swizzled 128-byte row = +32 bytes = +2 in the
-              // (>>4) start-address field
-              umma_bf16(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
-                        (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                // advancing 16 bf16 along K inside the swizzled 128-byte row = +32 bytes = +2 in the
+                // (>>4) start-address field
+                if constexpr (PAIR)
+                  umma_bf16_pair(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
+                                 (kb | k) != 0 ? 1u : 0u);
+                else
+                  umma_bf16(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
+                            (kb | k) != 0 ? 1u : 0u);
+              }
+            } else {
+              // fp32 emulation: x = hi + mid + lo (three bf16, 24 mantissa bits, exact), and
+              // g.q ~ g_hi(q_hi + q_mid + q_lo) + g_mid(q_hi + q_mid) + g_lo q_hi: six bf16 MMAs into one
+              // fp32 accumulator; the dropped terms are below 2^-24 of |g||q|.
+              constexpr int kTermA[6] = {0, 0, 1, 0, 1, 2};
+              constexpr int kTermB[6] = {0, 1, 0, 2, 1, 0};
+#pragma unroll
+              for (int term = 0; term < 6; ++term) {
+                const uint64_t adesc = make_sw128_desc(a_addr + kTermA[term] * kABytes);
+                const uint64_t bdesc = make_sw128_desc(a_addr + a_all + kTermB[term] * b_bytes);
+#pragma unroll
+                for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                  umma_bf16(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
+                            (kb | k | term) != 0 ? 1u : 0u);
+              }
             }
-          } else {
-            // fp32 emulation: x = hi + mid + lo (three bf16, 24 mantissa bits, exact), and
-            // g.q ~ g_hi(q_hi + q_mid + q_lo) + g_mid(q_hi + q_mid) + g_lo q_hi: six bf16 MMAs into one
-            // fp32 accumulator; the dropped terms are below 2^-24 of |g||q|.
-            constexpr int kTermA[6] = {0, 0, 1, 0, 1, 2};
-            constexpr int kTermB[6] = {0, 1, 0, 2, 1, 0};
-#pragma unroll
-            for (int term = 0; term < 6; ++term) {
-              const uint64_t adesc = make_sw128_desc(a_addr + kTermA[term] * kABytes);
-              const uint64_t bdesc = make_sw128_desc(a_addr + a_all + kTermB[term] * b_bytes);
-#pragma unroll
-              for (int k = 0; k < kBlockK / kUmmaK; ++k)
-                umma_bf16(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
-                          (kb | k | term) != 0 ? 1u : 0u);
+            // smem slot reusable (in both CTAs of a pair) once these MMAs retire
+            if constexpr (PAIR) umma_commit_pair(&sh->empty[stage]); else umma_commit(&sh->empty[stage]);
+            // accumulator complete (pair: each CTA's epilogue is told about its own half)
+            if (kb == cfg.k_blocks - 1) {
+              if constexpr (PAIR) umma_commit_pair(&sh->tmem_full[as]); else umma_commit(&sh->tmem_full[as]);
             }
           }
-          umma_commit(&sh->empty[stage]);   // smem slot reusable once these MMAs retire
+          __syncwarp();
           if (++stage == static_cast<uint32_t>(cfg.stages)) { stage = 0; phase ^= 1; }
         }
-        if (ok) umma_commit(&sh->tmem_full[as]);   // accumulator complete
         ++it;
       }
     }
@@ -216,11 +297,19 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
     const int c_begin = min(part * per_part, n_chunks) * 16;
     const int c_end = min((part + 1) * per_part, n_chunks) * 16;
     const int64_t last_row = p.n_rows - 1;
+    const uint32_t tmem_empty_leader = PAIR ? mapa_u32(smem_u32(&sh->tmem_empty[0]), 0) : 0u;
     uint32_t it = 0;
     bool ok = true;
-    for (int j = blockIdx.x; j < n_sel && ok; j += gridDim.x) {
+    for (int u = u_begin; u < n_units && ok; u += u_step) {
+      const Unit un = unit_of(u);
+      if (un.skip) continue;
+      const int j = un.j;
       const int t = j * inc;
-      if (exc != 0 && (t % exc) == 0) continue;
+      // queries of this unit and where their thresholds sit in shared memory
+      const int q0 = p.q0 + un.chunk * kMaxQ;
+      const int nq = min(p.nq - un.chunk * kMaxQ, kMaxQ);
+      const float* thr_s = sh->thr + (PAIR ? un.chunk * kMaxQ : 0);
+      const float* thr_raw_s = sh->thr_raw + (PAIR ? un.chunk * kMaxQ : 0);
       const uint32_t as = it & 1, aphase = (it >> 1) & 1;
       if (!mbar_wait(&sh->tmem_full[as], aphase, &sh->abort, flags)) break;
       tcgen05_fence_after();
@@ -228,8 +317,8 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
       const bool row_ok = row <= last_row;
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                               as * static_cast<uint32_t>(cfg.acc_stride);
-      if (MODE == kModeFilter && cfg.debug_skip_epilogue == 1) {
-        // mainloop-only timing: hand the accumulator straight back
+      if (!un.valid || (MODE == kModeFilter && cfg.debug_skip_epilogue == 1)) {
+        // nothing to read: a duplicate half tile, or mainloop-only timing
       } else if constexpr (MODE == kModeFilter) {
         // One sweep over the accumulator; a passing (column, score) is parked in this thread's
         // private shared-memory stash and the slots are claimed at the end of the tile, four
@@ -244,33 +333,33 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
             uint2 e[4];
             uint32_t pos[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (i0 + u < n_st) {
-                e[u] = my_stash[(i0 + u) * 32];
-                pos[u] = atomicAdd(p.cnt + q0 + e[u].x, 1u);
+            for (int u4 = 0; u4 < 4; ++u4)
+              if (i0 + u4 < n_st) {
+                e[u4] = my_stash[(i0 + u4) * 32];
+                pos[u4] = atomicAdd(p.cnt + q0 + e[u4].x, 1u);
               }
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (i0 + u < n_st && pos[u] < static_cast<uint32_t>(p.cap))
-                p.cand[static_cast<int64_t>(q0 + e[u].x) * p.cap + pos[u]] =
-                    make_key(__uint_as_float(e[u].y), static_cast<uint32_t>(row));
+            for (int u4 = 0; u4 < 4; ++u4)
+              if (i0 + u4 < n_st && pos[u4] < static_cast<uint32_t>(p.cap))
+                p.cand[static_cast<int64_t>(q0 + e[u4].x) * p.cap + pos[u4]] =
+                    make_key(__uint_as_float(e[u4].y), static_cast<uint32_t>(row));
           }
           n_st = 0;
         };
         auto process16 = [&](const uint32_t (&acc)[16], int c0) {
           // branch-free pass mask for the 16 columns (every taken branch would expose its full
           // latency), then a short loop over the set bits
-          const float4* thr4 = reinterpret_cast<const float4*>((raw_ok ? sh->thr_raw : sh->thr) + c0);
+          const float4* thr4 = reinterpret_cast<const float4*>((raw_ok ? thr_raw_s : thr_s) + c0);
           const float mul = raw_ok ? 1.0f : p.scale;
           uint32_t bits = 0;
 #pragma unroll
           for (int c4 = 0; c4 < 4; ++c4) {
-            const float4 t = thr4[c4];
-            const float tv[4] = {t.x, t.y, t.z, t.w};
+            const float4 tq = thr4[c4];
+            const float tv[4] = {tq.x, tq.y, tq.z, tq.w};
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const float a = __uint_as_float(acc[c4 * 4 + u]);
-              bits |= ((raw_ok ? a : a * mul) < tv[u]) ? 0u : (1u << (c4 * 4 + u));
+            for (int u4 = 0; u4 < 4; ++u4) {
+              const float a = __uint_as_float(acc[c4 * 4 + u4]);
+              bits |= ((raw_ok ? a : a * mul) < tv[u4]) ? 0u : (1u << (c4 * 4 + u4));
             }
           }
           if (!row_ok) bits = 0;
@@ -279,9 +368,9 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
             bits &= bits - 1;
             uint32_t a = acc[0];
 #pragma unroll
-            for (int u = 1; u < 16; ++u) a = (c == u) ? acc[u] : a;
+            for (int u4 = 1; u4 < 16; ++u4) a = (c == u4) ? acc[u4] : a;
             const float sc = __uint_as_float(a) * p.scale;
-            if (sc < sh->thr[c0 + c]) continue;        // the exact test
+            if (sc < thr_s[c0 + c]) continue;        // the exact test
             if (n_st == kStash) flush();
             my_stash[n_st * 32] = make_uint2(static_cast<uint32_t>(c0 + c), __float_as_uint(sc));
             ++n_st;
@@ -328,18 +417,31 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
       }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sh->tmem_empty[as]);
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_cluster(tmem_empty_leader + as * 8u);
+        else mbar_arrive(&sh->tmem_empty[as]);
+      }
       ++it;
     }
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) {
+    __syncwarp();
+    cluster_sync_all();   // neither CTA may retire while its peer can still signal or read it
+  } else {
+    __syncthreads();
+  }
   tcgen05_fence_after();
   if (warp == kAllocWarp) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"(static_cast<uint32_t>(cfg.tmem_cols))
-                 : "memory");
+    if constexpr (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                   "r"(static_cast<uint32_t>(cfg.tmem_cols))
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                   "r"(static_cast<uint32_t>(cfg.tmem_cols))
+                   : "memory");
   }
 }
 
@@ -358,18 +460,15 @@ cudaError_t launch_scan_mma(const ScanParams& p, const __nv_bfloat16* q_bf16, in
   if (split != 1 && split != 3) return cudaErrorInvalidValue;
   if (split == 3 && p.nq > kSplitMaxQ) return cudaErrorInvalidValue;
   if (p.n_rows > 0x7fffffffll - kBlockM) return cudaErrorInvalidValue;   // TMA coordinates are int32
+  if (p.sched.tile_exc != 0 && p.sched.tile_exc % p.sched.tile_inc != 0) return cudaErrorInvalidValue;
   MmaCfg cfg;
   cfg.n_umma = n_qchunks > 1 ? kMaxQ : (p.nq + 15) / 16 * 16;   // multi-chunk launches: full-width tiles (padded columns never pass)
   cfg.k_blocks = (p.dim + kBlockK - 1) / kBlockK;
-  int cols = 32;
-  while (cols < 2 * cfg.n_umma) cols <<= 1;
-  cfg.tmem_cols = cols;
-  cfg.acc_stride = cols / 2;
   cfg.split = split;
   cfg.g_plane_rows = p.n_rows;
   cfg.q_plane_rows = n_q_padded;
+  cfg.n_qchunks = n_qchunks;
   cfg.debug_skip_epilogue = getenv("MMRS_K2_DEBUG_SKIP_EPI") ? atoi(getenv("MMRS_K2_DEBUG_SKIP_EPI")) : 0;   // 1: no epilogue, 2: nothing passes
-  const size_t stage_bytes = split * (static_cast<size_t>(kABytes) + static_cast<size_t>(cfg.n_umma) * kBlockK * 2);
   // Up to 128 queries the CTA is sized so that TWO fit on an SM (<= 113 KB of shared memory, 80
   // registers x 384 threads, <= 256 TMEM columns each): the scans of two searches in flight on
   // different streams then share the HBM stream instead of queueing behind each other, and the
@@ -377,12 +476,22 @@ cudaError_t launch_scan_mma(const ScanParams& p, const __nv_bfloat16* q_bf16, in
   int small_max = 128;   // 33..128 queries: 3-4 ring stages per CTA, two CTAs per SM
   if (const char* e = getenv("MMRS_K2_SMALL_MAX")) small_max = atoi(e);
   const bool small = split == 1 && cfg.n_umma <= small_max && getenv("MMRS_K2_BIG_SMEM") == nullptr;
-  const size_t budget = (small ? 113 * 1024 : 227 * 1024) - sizeof(MmaShared) - 1024 - (small ? 1024 : 0);
+  // Above that the kernel is tensor-bound and runs as CTA pairs (cta_group::2, see the file header)
+  const bool pair = !small && split == 1 && cfg.n_umma > 128 && getenv("MMRS_K2_NO_PAIR") == nullptr;
+  if (pair) cfg.n_umma = (cfg.n_umma + 31) / 32 * 32;   // each CTA stages half the query rows
+  int cols = 32;
+  while (cols < 2 * cfg.n_umma) cols <<= 1;
+  cfg.tmem_cols = cols;
+  cfg.acc_stride = cols / 2;
+  const int b_rows = pair ? cfg.n_umma / 2 : cfg.n_umma;
+  const size_t stage_bytes = split * (static_cast<size_t>(kABytes) + static_cast<size_t>(b_rows) * kBlockK * 2);
+  const size_t shared_struct = pair ? sizeof(MmaSharedT<kMaxQChunks>) : sizeof(MmaShared);
+  const size_t budget = (small ? 113 * 1024 : 227 * 1024) - shared_struct - 1024 - (small ? 1024 : 0);
   int stages = static_cast<int>(budget / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return cudaErrorInvalidValue;
   cfg.stages = stages;
-  const size_t smem = 1024 + stage_bytes * stages + sizeof(MmaShared);
+  const size_t smem = 1024 + stage_bytes * stages + shared_struct;
 
   CUtensorMap map_g, map_q;
   if (static_cast<int64_t>(split) * p.n_rows > 0x7fffffffll - kBlockM) return cudaErrorInvalidValue;
@@ -390,33 +499,53 @@ cudaError_t launch_scan_mma(const ScanParams& p, const __nv_bfloat16* q_bf16, in
                 static_cast<uint64_t>(p.ld), kBlockM))
     return cudaErrorNotSupported;
   if (!make_map(&map_q, q_bf16, static_cast<uint64_t>(split) * n_q_padded, static_cast<uint64_t>(p.ldq),
-                static_cast<uint64_t>(p.ldq), static_cast<uint32_t>(cfg.n_umma)))
+                static_cast<uint64_t>(p.ldq), static_cast<uint32_t>(b_rows)))
     return cudaErrorNotSupported;
 
-  // 33..64 queries: the small-footprint CTA has only 4 ring stages, so one launch fills both CTA
-  // slots of every SM itself (measured: 0.202 vs 0.224 ms per step at 64 queries)
-  int ctas_per_sm = (small && cfg.n_umma > 32) ? 2 : 1;
-  if (const char* e = getenv("MMRS_K2_CTAS_PER_SM")) ctas_per_sm = atoi(e) == 2 && small ? 2 : 1;
-  int grid = sm_count * ctas_per_sm / n_qchunks;
-  if (grid > p.sched.n_sel) grid = p.sched.n_sel;
-  if (grid < 1) grid = 1;
+  const int R = p.sched.tile_exc ? p.sched.tile_exc / p.sched.tile_inc : 0;
+  const int n_valid = R == 1 ? 0 : (R ? p.sched.n_sel - (p.sched.n_sel + R - 1) / R : p.sched.n_sel);
+  if (n_valid < 1) return cudaSuccess;   // nothing to visit
+  dim3 grid;
+  if (pair) {
+    // one pair per TPC; units = (tile pair, query chunk)
+    const int n_units = (n_valid + 1) / 2 * n_qchunks;
+    int pairs = sm_count / 2;
+    if (pairs > n_units) pairs = n_units;
+    grid = dim3(2 * pairs, 1);
+  } else {
+    // 33..64 queries: the small-footprint CTA has only 4 ring stages, so one launch fills both CTA
+    // slots of every SM itself (measured: 0.202 vs 0.224 ms per step at 64 queries)
+    int ctas_per_sm = (small && cfg.n_umma > 32) ? 2 : 1;
+    if (const char* e = getenv("MMRS_K2_CTAS_PER_SM")) ctas_per_sm = atoi(e) == 2 && small ? 2 : 1;
+    int gx = sm_count * ctas_per_sm / n_qchunks;
+    if (gx > p.sched.n_sel) gx = p.sched.n_sel;
+    if (gx < 1) gx = 1;
+    grid = dim3(gx, n_qchunks);
+  }
   auto go = [&](auto kernel) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    return launch_pdl(kernel, dim3(grid, n_qchunks), dim3((kCtrlWarps + (small ? 8 : 16)) * 32), smem, stream, map_g, map_q, p,
-                      cfg, flags);
+    return launch_pdl_cluster(kernel, grid, dim3((kCtrlWarps + (small ? 8 : 16)) * 32), smem, stream, pair ? 2u : 1u,
+                              map_g, map_q, p, cfg, flags);
   };
   if (small) {
     switch (mode) {
-      case kModeScores: return go(scan_mma_kernel<kModeScores, 8>);
-      case kModeDense: return go(scan_mma_kernel<kModeDense, 8>);
-      default: return go(scan_mma_kernel<kModeFilter, 8>);
+      case kModeScores: return go(scan_mma_kernel<kModeScores, 8, false>);
+      case kModeDense: return go(scan_mma_kernel<kModeDense, 8, false>);
+      default: return go(scan_mma_kernel<kModeFilter, 8, false>);
     }
   }
-  switch (mode) {   // > 128 queries: tensor-bound, one CTA per SM, 16 epilogue warps
-    case kModeScores: return go(scan_mma_kernel<kModeScores, 16>);
-    case kModeDense: return go(scan_mma_kernel<kModeDense, 16>);
-    default: return go(scan_mma_kernel<kModeFilter, 16>);
+  if (pair) {
+    switch (mode) {   // > 128 queries: tensor-bound, one CTA per SM, CTA pairs, 16 epilogue warps each
+      case kModeScores: return go(scan_mma_kernel<kModeScores, 16, true>);
+      case kModeDense: return go(scan_mma_kernel<kModeDense, 16, true>);
+      default: return go(scan_mma_kernel<kModeFilter, 16, true>);
+    }
+  }
+  switch (mode) {   // fp32 emulation (three planes per operand) and MMRS_K2_NO_PAIR
+    case kModeScores: return go(scan_mma_kernel<kModeScores, 16, false>);
+    case kModeDense: return go(scan_mma_kernel<kModeDense, 16, false>);
+    default: return go(scan_mma_kernel<kModeFilter, 16, false>);
   }
 }
 

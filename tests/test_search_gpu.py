@@ -255,6 +255,36 @@ def test_mma_path_matches_oracle(mm, oracle, n, d, nq, k):
     check_bf16(mm, oracle, g, q, k, "mma")
 
 
+@pytest.mark.parametrize("n,d,nq,k", [
+    (70_001, 512, 130, 100),     # UMMA N = 160: each CTA of the pair stages 80 query rows
+    (40_000, 768, 200, 50),      # N = 224
+    (8_321, 64, 700, 5),         # three query chunks as work units, odd tile count, few tiles
+    (33_000, 520, 1024, 10),     # four chunks
+    (129, 64, 129, 3),           # two tiles = one pair, single phase
+    (128, 64, 256, 128),         # one tile: the second CTA of the pair has nothing to read
+])
+def test_mma_cta_pair_mode_matches_oracle(mm, oracle, n, d, nq, k):
+    """More than 128 queries run as CTA pairs (tcgen05.mma.cta_group::2, M = 256)."""
+    g = oracle.synthetic_gallery(n, d, seed=(n + d) % 89, dtype=torch.bfloat16)
+    q = oracle.synthetic_queries(nq, d, seed=nq)
+    check_bf16(mm, oracle, g, q, k, "mma")
+
+
+def test_mma_cta_pair_and_single_cta_agree_bitwise(mm, oracle, monkeypatch):
+    g = oracle.synthetic_gallery(90_000, 512, seed=8, dtype=torch.bfloat16)
+    gal = mm.DeviceGallery(g)
+    q = bf16_unit_queries(oracle.synthetic_queries(600, 512, seed=4))
+    v2, i2 = mm.search_topk(q, gal, 100, path="mma", normalize_queries=False)
+    s2 = mm.full_scores(q[:200], gal, path="mma", normalize_queries=False)
+    monkeypatch.setenv("MMRS_K2_NO_PAIR", "1")
+    v1, i1 = mm.search_topk(q, gal, 100, path="mma", normalize_queries=False)
+    s1 = mm.full_scores(q[:200], gal, path="mma", normalize_queries=False)
+    assert torch.equal(v1, v2) and torch.equal(i1, i2)     # same MMA shapes along K, same accumulation order
+    assert torch.equal(s1, s2)
+    want = oracle.full_scores(q[:200], g, mode="bf16", normalize_queries=False)
+    np.testing.assert_allclose(s2.cpu().numpy(), want.numpy(), atol=1e-5, rtol=0)
+
+
 def test_mma_and_gemv_paths_agree_bitwise_on_indices(mm, oracle):
     g = oracle.synthetic_gallery(150_000, 512, seed=6, dtype=torch.bfloat16)
     gal = mm.DeviceGallery(g)
