@@ -2,8 +2,11 @@
 //
 // N(N-1)/2 dot products is a GEMM (5.0e13 pairs at N = 10 M), so the
 // candidate pass runs on the 5th-gen tensor cores over a bf16 copy of the unit-norm embeddings:
-//   S[128 rows i, 256 rows j] = X16[i-block] * X16[j-block]^T      (tcgen05.mma, M=128, N=256)
-// and the epilogue keeps pairs (i < j) with S >= tau - margin.  Rounding unit rows to bf16 moves a
+//   S[256 rows i, 256 rows j] = X16[i-blocks] * X16[j-block]^T     (tcgen05.mma.cta_group::2, M=256, N=256)
+// by a PAIR of CTAs (one TPC): each CTA stages its own 128-row i-block and half of the j-block,
+// CTA 0's MMA warp issues for both, each CTA's 128 x 256 accumulator lands in its own TMEM (with one
+// SM per MMA the tensor pipe waits for shared-memory operands a third of the time, see scan_mma.cu);
+// the epilogue keeps pairs (i < j) with S >= tau - margin.  Rounding unit rows to bf16 moves a
 // dot product by at most ||a|| ||b - b^|| + ||a - a^|| ||b^|| <= 2 * 2^-9 (1 + 2^-9) < 0.004
 // (Cauchy-Schwarz; round-to-nearest is within 2^-9 relative per element), so with margin >= 0.004
 // every true pair survives; the few survivors are then re-scored in fp32 with exactly the
@@ -22,10 +25,10 @@ constexpr int kSjmThreads = 256;
 constexpr int kSjmBM = 128;
 constexpr int kSjmBN = 256;
 constexpr int kSjmBK = 64;
-constexpr int kSjmStages = 4;
+constexpr int kSjmStages = 6;
 constexpr int kSjmPanel = 8;   // j-blocks per panel
 constexpr int kSjmABytes = kSjmBM * kSjmBK * 2;
-constexpr int kSjmBBytes = kSjmBN * kSjmBK * 2;
+constexpr int kSjmBBytes = (kSjmBN / 2) * kSjmBK * 2;   // per CTA: half of the j-block's rows
 constexpr int kSjmStageBytes = kSjmABytes + kSjmBBytes;
 
 struct SjmShared {
@@ -51,7 +54,9 @@ struct SjmParams {
   unsigned long long* cand_count;
 };
 
-// tile number -> (i-block, j-block); returns false for tiles that lie entirely on/below the diagonal
+// pair-tile number -> (first of the pair's two i-blocks, j-block); returns false when even the
+// first i-block lies entirely on/below the diagonal (then so does the second).  When only the
+// second does, its CTA computes a tile whose columns all fail the epilogue's j > i test.
 __device__ __forceinline__ bool sjm_decode(const SjmParams& p, int64_t t, int64_t& ib, int64_t& jb) {
   int lo = 0, hi = p.n_my_panels;           // last m with panel_start[m] <= t
   while (hi - lo > 1) {
@@ -62,7 +67,7 @@ __device__ __forceinline__ bool sjm_decode(const SjmParams& p, int64_t t, int64_
   const int64_t u = t - p.panel_start[lo];
   int64_t nj = p.nbj - panel * kSjmPanel;
   if (nj > kSjmPanel) nj = kSjmPanel;
-  ib = u / nj;
+  ib = 2 * (u / nj);
   jb = panel * kSjmPanel + u % nj;
   return jb * kSjmBN + (kSjmBN - 1) > ib * kSjmBM;
 }
@@ -74,120 +79,137 @@ selfjoin_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   SjmShared* sh = reinterpret_cast<SjmShared*>(ring + kSjmStages * kSjmStageBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();                 // 0: pair leader
+  const int64_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kSjmStages; ++s) { mbar_init(&sh->full[s], 1); mbar_init(&sh->empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&sh->tmem_full[a], 1); mbar_init(&sh->tmem_empty[a], 4); }
+    // the leader's tmem_empty collects the four epilogue warps of both CTAs
+    for (int a = 0; a < 2; ++a) { mbar_init(&sh->tmem_full[a], 1); mbar_init(&sh->tmem_empty[a], 8); }
     sh->abort = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)),
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)),
                  "r"(512u)
                  : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   tcgen05_fence_before();
-  __syncthreads();
+  __syncwarp();
+  cluster_sync_all();   // the peer's barriers exist before anything is signalled across
   tcgen05_fence_after();
   const uint32_t tmem_base = sh->tmem_base;
 
   if (warp == 0) {
-    if (lane == 0) {   // ===== TMA producer =====
+    if (lane == 0) {   // ===== TMA producer (both CTAs; bytes are credited to the leader's barrier) =====
       uint32_t stage = 0, phase = 0;
       bool ok = true;
-      for (int64_t t = blockIdx.x; t < p.total_tiles && ok; t += gridDim.x) {
+      for (int64_t t = pair; t < p.total_tiles && ok; t += n_pairs) {
         int64_t ib, jb;
         if (!sjm_decode(p, t, ib, jb)) continue;
+        const int32_t a_row = static_cast<int32_t>((ib + rank) * kSjmBM);   // past the last block: zero-filled
+        const int32_t b_row = static_cast<int32_t>(jb * kSjmBN + rank * (kSjmBN / 2));
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           if (!mbar_wait(&sh->empty[stage], phase ^ 1, &sh->abort, flags)) { ok = false; break; }
           uint8_t* a_dst = ring + static_cast<size_t>(stage) * kSjmStageBytes;
-          mbar_expect_tx(&sh->full[stage], kSjmStageBytes);
-          tma_load_2d(a_dst, &map_a, &sh->full[stage], kb * kSjmBK, static_cast<int32_t>(ib * kSjmBM), kEvictLast);
-          tma_load_2d(a_dst + kSjmABytes, &map_b, &sh->full[stage], kb * kSjmBK,
-                      static_cast<int32_t>(jb * kSjmBN), kEvictLast);
+          const uint32_t full_leader = mapa_u32(smem_u32(&sh->full[stage]), 0);
+          if (rank == 0) mbar_expect_tx(&sh->full[stage], 2 * kSjmStageBytes);
+          tma_load_2d_pair(a_dst, &map_a, full_leader, kb * kSjmBK, a_row, kEvictLast);
+          tma_load_2d_pair(a_dst + kSjmABytes, &map_b, full_leader, kb * kSjmBK, b_row, kEvictLast);
           if (++stage == kSjmStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {   // ===== MMA issuer =====
-      const uint32_t idesc = make_idesc(kSjmBN);
+    // ===== MMA issuer: the leader's whole warp walks the loop, one elected lane issues (descriptors
+    // stay in uniform registers; with the loop inside `if (lane == 0)` the issue sequence, not the
+    // tensor pipe, set the pace -- see scan_mma.cu) =====
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc(kSjmBN, 256u);
+      const uint32_t ring_addr = smem_u32(ring);
       uint32_t stage = 0, phase = 0, it = 0;
       bool ok = true;
-      for (int64_t t = blockIdx.x; t < p.total_tiles && ok; t += gridDim.x) {
+      for (int64_t t = pair; t < p.total_tiles && ok; t += n_pairs) {
         int64_t ib, jb;
         if (!sjm_decode(p, t, ib, jb)) continue;
         const uint32_t as = it & 1, aphase = (it >> 1) & 1;
-        if (!mbar_wait(&sh->tmem_empty[as], aphase ^ 1, &sh->abort, flags)) break;
+        if (!__all_sync(0xffffffffu, mbar_wait(&sh->tmem_empty[as], aphase ^ 1, &sh->abort, flags))) break;
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + as * kSjmBN;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
-          if (!mbar_wait(&sh->full[stage], phase, &sh->abort, flags)) { ok = false; break; }
+          if (!__all_sync(0xffffffffu, mbar_wait(&sh->full[stage], phase, &sh->abort, flags))) { ok = false; break; }
           tcgen05_fence_after();
-          const uint32_t a_addr = smem_u32(ring + static_cast<size_t>(stage) * kSjmStageBytes);
-          const uint64_t adesc = make_sw128_desc(a_addr);
-          const uint64_t bdesc = make_sw128_desc(a_addr + kSjmABytes);
+          const uint32_t a_addr = ring_addr + stage * kSjmStageBytes;
+          if (elect_one()) {
+            const uint64_t adesc = make_sw128_desc(a_addr);
+            const uint64_t bdesc = make_sw128_desc(a_addr + kSjmABytes);
 #pragma unroll
-          for (int k = 0; k < kSjmBK / 16; ++k)
-            umma_bf16(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
-                      (kb | k) != 0 ? 1u : 0u);
-          umma_commit(&sh->empty[stage]);
+            for (int k = 0; k < kSjmBK / 16; ++k)
+              umma_bf16_pair(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
+                             (kb | k) != 0 ? 1u : 0u);
+            umma_commit_pair(&sh->empty[stage]);
+            if (kb == p.k_blocks - 1) umma_commit_pair(&sh->tmem_full[as]);
+          }
+          __syncwarp();
           if (++stage == kSjmStages) { stage = 0; phase ^= 1; }
         }
-        if (ok) umma_commit(&sh->tmem_full[as]);
         ++it;
       }
     }
   } else if (warp >= 4) {
     // ===== epilogue: keep (i < j) with S >= tau - margin =====
     const int ew = warp - 4;
+    const uint32_t tmem_empty_leader = mapa_u32(smem_u32(&sh->tmem_empty[0]), 0);
     uint32_t it = 0;
-    for (int64_t t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+    for (int64_t t = pair; t < p.total_tiles; t += n_pairs) {
       int64_t ib, jb;
       if (!sjm_decode(p, t, ib, jb)) continue;
       const uint32_t as = it & 1, aphase = (it >> 1) & 1;
       if (!mbar_wait(&sh->tmem_full[as], aphase, &sh->abort, flags)) break;
       tcgen05_fence_after();
-      const int64_t i = ib * kSjmBM + ew * 32 + lane;
+      const int64_t i = (ib + rank) * kSjmBM + ew * 32 + lane;
       const int64_t j0 = jb * kSjmBN;
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * kSjmBN;
-      // columns at or left of the diagonal can never give j > i: skip whole chunks there
-      for (int c0 = 0; c0 < kSjmBN; c0 += 16) {
-        uint32_t acc[16];
-        __syncwarp();
-        tmem_ld16(taddr0 + static_cast<uint32_t>(c0), acc);
-        tmem_ld_wait();
-        uint32_t bits = 0;
+      // a warp whose 32 rows all lie at or beyond the j-block's last column has nothing to keep
+      if ((ib + rank) * kSjmBM + ew * 32 < j0 + kSjmBN - 1) {
+        for (int c0 = 0; c0 < kSjmBN; c0 += 16) {
+          uint32_t acc[16];
+          __syncwarp();
+          tmem_ld16(taddr0 + static_cast<uint32_t>(c0), acc);
+          tmem_ld_wait();
+          uint32_t bits = 0;
 #pragma unroll
-        for (int c = 0; c < 16; ++c) bits |= (__uint_as_float(acc[c]) >= p.thr_lo) ? (1u << c) : 0u;
-        while (bits) {
-          const int c = __ffs(bits) - 1;
-          bits &= bits - 1;
-          const int64_t j = j0 + c0 + c;
-          if (j > i && j < p.n_rows) {   // i < j < n_rows
-            const unsigned long long pos = atomicAdd(p.cand_count, 1ull);
-            if (pos < static_cast<unsigned long long>(p.cand_cap)) {
-              p.cand[2 * pos] = i;
-              p.cand[2 * pos + 1] = j;
+          for (int c = 0; c < 16; ++c) bits |= (__uint_as_float(acc[c]) >= p.thr_lo) ? (1u << c) : 0u;
+          while (bits) {
+            const int c = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const int64_t j = j0 + c0 + c;
+            if (j > i && j < p.n_rows) {   // i < j < n_rows
+              const unsigned long long pos = atomicAdd(p.cand_count, 1ull);
+              if (pos < static_cast<unsigned long long>(p.cand_cap)) {
+                p.cand[2 * pos] = i;
+                p.cand[2 * pos + 1] = j;
+              }
             }
           }
         }
       }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sh->tmem_empty[as]);
+      if (lane == 0) mbar_arrive_cluster(tmem_empty_leader + as * 8u);
       ++it;
     }
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  __syncwarp();
+  cluster_sync_all();   // neither CTA may retire while its peer can still signal or read it
   tcgen05_fence_after();
   if (warp == 2)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
 // Exact fp32 re-score of the candidates: the same single fmaf chain, k ascending, as
@@ -230,7 +252,7 @@ int64_t sjm_plan(int64_t n_rows, int32_t rank, int32_t world, int64_t* h_panel_s
     if (ni > nbi) ni = nbi;
     int64_t nj = nbj - pnl * kSjmPanel;
     if (nj > kSjmPanel) nj = kSjmPanel;
-    tiles += ni * nj;
+    tiles += (ni + 1) / 2 * nj;   // a CTA pair takes two i-blocks at a time
   }
   if (h_panel_start) h_panel_start[m] = tiles;
   *n_my_panels = m;
@@ -264,16 +286,22 @@ cudaError_t launch_selfjoin_mma(const __nv_bfloat16* emb16, int64_t n_rows, int3
   CUtensorMap map_a, map_b;
   if (!make_map(&map_a, emb16, static_cast<uint64_t>(n_rows), static_cast<uint64_t>(dim), static_cast<uint64_t>(ld16), kSjmBM))
     return cudaErrorNotSupported;
-  if (!make_map(&map_b, emb16, static_cast<uint64_t>(n_rows), static_cast<uint64_t>(dim), static_cast<uint64_t>(ld16), kSjmBN))
+  if (!make_map(&map_b, emb16, static_cast<uint64_t>(n_rows), static_cast<uint64_t>(dim), static_cast<uint64_t>(ld16), kSjmBN / 2))
     return cudaErrorNotSupported;
   const size_t smem = 1024 + static_cast<size_t>(kSjmStages) * kSjmStageBytes + sizeof(SjmShared);
   cudaError_t e = cudaFuncSetAttribute(selfjoin_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem));
   if (e != cudaSuccess) return e;
-  int64_t grid = sm_count;
-  if (grid > total_tiles) grid = total_tiles;
-  selfjoin_mma_kernel<<<static_cast<int>(grid), kSjmThreads, smem, stream>>>(map_a, map_b, p, flags);
-  return cudaGetLastError();
+  int64_t pairs = sm_count / 2;          // one CTA pair per TPC
+  if (pairs > total_tiles) pairs = total_tiles;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(2 * pairs)); cfg.blockDim = dim3(kSjmThreads);
+  cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, selfjoin_mma_kernel, map_a, map_b, p, flags);
 }
 
 cudaError_t launch_selfjoin_recheck(const int64_t* cand, int64_t n_cand, const float* emb, int64_t ld, int32_t dim,
