@@ -29,11 +29,12 @@ cudaError_t launch_threshold_sweep_labeled(const float* scores, const int64_t* t
                                            unsigned long long* hist_ws, uint32_t* mm_ws, int sm_count,
                                            cudaStream_t stream);
 // K5 on tensor cores (selfjoin_mma.cu)
-int64_t sjm_plan(int64_t n_rows, int32_t rank, int32_t world, int64_t* h_panel_start, int32_t max_panels,
+bool sjm_pair_mode(int64_t n_rows, int32_t dim, int32_t world);
+int64_t sjm_plan(int64_t n_rows, int32_t rank, int32_t world, bool pair, int64_t* h_panel_start, int32_t max_panels,
                  int32_t* n_my_panels);
 int64_t sjm_max_panels(int64_t n_rows);
 cudaError_t launch_selfjoin_mma(const __nv_bfloat16* emb16, int64_t n_rows, int32_t dim, int64_t ld16,
-                                float thr_lo, int32_t rank, int32_t world, const int64_t* d_panel_start,
+                                float thr_lo, int32_t rank, int32_t world, bool pair, const int64_t* d_panel_start,
                                 int32_t n_my_panels, int64_t total_tiles, int64_t* cand, int64_t cand_cap,
                                 unsigned long long* cand_count, int32_t* flags, int sm_count,
                                 cudaStream_t stream);
@@ -1006,13 +1007,14 @@ int mmrs_selfjoin_pairs_tc(const float* d_emb_f32, int64_t ld_f32, const void* d
 
   std::vector<int64_t> h_panel(static_cast<size_t>(max_panels) + 1);
   int32_t n_my = 0;
-  const int64_t tiles = sjm_plan(n_rows, rank, world, h_panel.data(), static_cast<int32_t>(max_panels), &n_my);
+  const bool pair = sjm_pair_mode(n_rows, dim, world);
+  const int64_t tiles = sjm_plan(n_rows, rank, world, pair, h_panel.data(), static_cast<int32_t>(max_panels), &n_my);
   MMRS_CUDA(cudaMemsetAsync(b, 0, 512, stream));
   MMRS_CUDA(cudaMemcpyAsync(d_panel, h_panel.data(), static_cast<size_t>(n_my + 1) * sizeof(int64_t),
                             cudaMemcpyHostToDevice, stream));
   MMRS_CUDA(cudaStreamSynchronize(stream));   // h_panel is pageable and goes out of scope
   MMRS_LAUNCH(launch_selfjoin_mma(static_cast<const __nv_bfloat16*>(d_emb_bf16), n_rows, dim, ld_bf16,
-                                  threshold - margin, rank, world, d_panel, n_my, tiles, cand, cand_capacity,
+                                  threshold - margin, rank, world, pair, d_panel, n_my, tiles, cand, cand_capacity,
                                   counts + 1, flags, dev.sm_count, stream));
   int32_t* h = pinned_status();
   if (!h) return fail(MMRS_ERR_CUDA, "cudaHostAlloc for the status word failed");

@@ -17,6 +17,8 @@
 // D = 512, L2 resident); inside a panel tiles are numbered j-fastest, so CTAs that run together
 // share their A rows and the B panel through L2.  Panels are dealt round-robin to the ranks of a
 // multi-GPU run (work per panel grows linearly with its index, so cyclic dealing balances).
+#include <stdlib.h>
+
 #include "tcgen05_utils.cuh"
 
 namespace mmrs {
@@ -25,15 +27,19 @@ constexpr int kSjmThreads = 256;
 constexpr int kSjmBM = 128;
 constexpr int kSjmBN = 256;
 constexpr int kSjmBK = 64;
-constexpr int kSjmStages = 6;
+constexpr int kSjmMaxStages = 6;
 constexpr int kSjmPanel = 8;   // j-blocks per panel
 constexpr int kSjmABytes = kSjmBM * kSjmBK * 2;
-constexpr int kSjmBBytes = (kSjmBN / 2) * kSjmBK * 2;   // per CTA: half of the j-block's rows
-constexpr int kSjmStageBytes = kSjmABytes + kSjmBBytes;
+// B rows a CTA stages per k-block: the whole j-block, or half of it in pair mode; ring depth to match
+template <bool PAIR> struct SjmCfg {
+  static constexpr int kBBytes = (PAIR ? kSjmBN / 2 : kSjmBN) * kSjmBK * 2;
+  static constexpr int kStageBytes = kSjmABytes + kBBytes;
+  static constexpr int kStages = PAIR ? 6 : 4;
+};
 
 struct SjmShared {
-  uint64_t full[kSjmStages];
-  uint64_t empty[kSjmStages];
+  uint64_t full[kSjmMaxStages];
+  uint64_t empty[kSjmMaxStages];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
@@ -49,14 +55,16 @@ struct SjmParams {
   int32_t panel_begin, panel_stride;
   const int64_t* panel_start;      // [n_my_panels + 1] first tile number of each of my panels
   int64_t total_tiles;
+  int32_t ib_per_tile;             // i-blocks per work unit: 2 in pair mode, else 1
   int64_t* cand;                   // [cand_cap, 2]
   int64_t cand_cap;
   unsigned long long* cand_count;
 };
 
-// pair-tile number -> (first of the pair's two i-blocks, j-block); returns false when even the
-// first i-block lies entirely on/below the diagonal (then so does the second).  When only the
-// second does, its CTA computes a tile whose columns all fail the epilogue's j > i test.
+// work-unit number -> (first i-block of the unit, j-block); returns false when that i-block lies
+// entirely on/below the diagonal.  In pair mode a unit is two i-blocks: if the first is below the
+// diagonal so is the second; when only the second is, its CTA computes a tile whose columns all
+// fail the epilogue's j > i test.
 __device__ __forceinline__ bool sjm_decode(const SjmParams& p, int64_t t, int64_t& ib, int64_t& jb) {
   int lo = 0, hi = p.n_my_panels;           // last m with panel_start[m] <= t
   while (hi - lo > 1) {
@@ -67,39 +75,54 @@ __device__ __forceinline__ bool sjm_decode(const SjmParams& p, int64_t t, int64_
   const int64_t u = t - p.panel_start[lo];
   int64_t nj = p.nbj - panel * kSjmPanel;
   if (nj > kSjmPanel) nj = kSjmPanel;
-  ib = 2 * (u / nj);
+  ib = p.ib_per_tile * (u / nj);
   jb = panel * kSjmPanel + u % nj;
   return jb * kSjmBN + (kSjmBN - 1) > ib * kSjmBM;
 }
 
+template <bool PAIR>
 __global__ void __launch_bounds__(kSjmThreads, 1)
 selfjoin_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const SjmParams p, int32_t* flags) {
+  constexpr int kSjmStages = SjmCfg<PAIR>::kStages;
+  constexpr int kSjmStageBytes = SjmCfg<PAIR>::kStageBytes;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   SjmShared* sh = reinterpret_cast<SjmShared*>(ring + kSjmStages * kSjmStageBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();                 // 0: pair leader
-  const int64_t pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;     // 0: pair leader
+  // work units of this CTA (pair): pair, pair + n_pairs, ...
+  const int64_t pair = PAIR ? blockIdx.x >> 1 : blockIdx.x, n_pairs = PAIR ? gridDim.x >> 1 : gridDim.x;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kSjmStages; ++s) { mbar_init(&sh->full[s], 1); mbar_init(&sh->empty[s], 1); }
-    // the leader's tmem_empty collects the four epilogue warps of both CTAs
-    for (int a = 0; a < 2; ++a) { mbar_init(&sh->tmem_full[a], 1); mbar_init(&sh->tmem_empty[a], 8); }
+    // pair mode: the leader's tmem_empty collects the four epilogue warps of both CTAs
+    for (int a = 0; a < 2; ++a) { mbar_init(&sh->tmem_full[a], 1); mbar_init(&sh->tmem_empty[a], PAIR ? 8 : 4); }
     sh->abort = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)),
-                 "r"(512u)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    if constexpr (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)),
+                   "r"(512u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)),
+                   "r"(512u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tcgen05_fence_before();
-  __syncwarp();
-  cluster_sync_all();   // the peer's barriers exist before anything is signalled across
+  if constexpr (PAIR) {
+    __syncwarp();
+    cluster_sync_all();   // the peer's barriers exist before anything is signalled across
+  } else {
+    __syncthreads();
+  }
   tcgen05_fence_after();
   const uint32_t tmem_base = sh->tmem_base;
 
@@ -115,10 +138,16 @@ selfjoin_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           if (!mbar_wait(&sh->empty[stage], phase ^ 1, &sh->abort, flags)) { ok = false; break; }
           uint8_t* a_dst = ring + static_cast<size_t>(stage) * kSjmStageBytes;
-          const uint32_t full_leader = mapa_u32(smem_u32(&sh->full[stage]), 0);
-          if (rank == 0) mbar_expect_tx(&sh->full[stage], 2 * kSjmStageBytes);
-          tma_load_2d_pair(a_dst, &map_a, full_leader, kb * kSjmBK, a_row, kEvictLast);
-          tma_load_2d_pair(a_dst + kSjmABytes, &map_b, full_leader, kb * kSjmBK, b_row, kEvictLast);
+          if constexpr (PAIR) {
+            const uint32_t full_leader = mapa_u32(smem_u32(&sh->full[stage]), 0);
+            if (rank == 0) mbar_expect_tx(&sh->full[stage], 2 * kSjmStageBytes);
+            tma_load_2d_pair(a_dst, &map_a, full_leader, kb * kSjmBK, a_row, kEvictLast);
+            tma_load_2d_pair(a_dst + kSjmABytes, &map_b, full_leader, kb * kSjmBK, b_row, kEvictLast);
+          } else {
+            mbar_expect_tx(&sh->full[stage], kSjmStageBytes);
+            tma_load_2d(a_dst, &map_a, &sh->full[stage], kb * kSjmBK, a_row, kEvictLast);
+            tma_load_2d(a_dst + kSjmABytes, &map_b, &sh->full[stage], kb * kSjmBK, b_row, kEvictLast);
+          }
           if (++stage == kSjmStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -128,7 +157,7 @@ selfjoin_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     // stay in uniform registers; with the loop inside `if (lane == 0)` the issue sequence, not the
     // tensor pipe, set the pace -- see scan_mma.cu) =====
     if (rank == 0) {
-      const uint32_t idesc = make_idesc(kSjmBN, 256u);
+      const uint32_t idesc = make_idesc(kSjmBN, PAIR ? 256u : 128u);
       const uint32_t ring_addr = smem_u32(ring);
       uint32_t stage = 0, phase = 0, it = 0;
       bool ok = true;
@@ -147,11 +176,18 @@ selfjoin_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             const uint64_t adesc = make_sw128_desc(a_addr);
             const uint64_t bdesc = make_sw128_desc(a_addr + kSjmABytes);
 #pragma unroll
-            for (int k = 0; k < kSjmBK / 16; ++k)
-              umma_bf16_pair(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
-                             (kb | k) != 0 ? 1u : 0u);
-            umma_commit_pair(&sh->empty[stage]);
-            if (kb == p.k_blocks - 1) umma_commit_pair(&sh->tmem_full[as]);
+            for (int k = 0; k < kSjmBK / 16; ++k) {
+              if constexpr (PAIR)
+                umma_bf16_pair(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
+                               (kb | k) != 0 ? 1u : 0u);
+              else
+                umma_bf16(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
+                          (kb | k) != 0 ? 1u : 0u);
+            }
+            if constexpr (PAIR) umma_commit_pair(&sh->empty[stage]); else umma_commit(&sh->empty[stage]);
+            if (kb == p.k_blocks - 1) {
+              if constexpr (PAIR) umma_commit_pair(&sh->tmem_full[as]); else umma_commit(&sh->tmem_full[as]);
+            }
           }
           __syncwarp();
           if (++stage == kSjmStages) { stage = 0; phase ^= 1; }
@@ -162,7 +198,7 @@ selfjoin_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   } else if (warp >= 4) {
     // ===== epilogue: keep (i < j) with S >= tau - margin =====
     const int ew = warp - 4;
-    const uint32_t tmem_empty_leader = mapa_u32(smem_u32(&sh->tmem_empty[0]), 0);
+    const uint32_t tmem_empty_leader = PAIR ? mapa_u32(smem_u32(&sh->tmem_empty[0]), 0) : 0u;
     uint32_t it = 0;
     for (int64_t t = pair; t < p.total_tiles; t += n_pairs) {
       int64_t ib, jb;
@@ -199,17 +235,28 @@ selfjoin_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(tmem_empty_leader + as * 8u);
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_cluster(tmem_empty_leader + as * 8u);
+        else mbar_arrive(&sh->tmem_empty[as]);
+      }
       ++it;
     }
   }
 
   tcgen05_fence_before();
-  __syncwarp();
-  cluster_sync_all();   // neither CTA may retire while its peer can still signal or read it
+  if constexpr (PAIR) {
+    __syncwarp();
+    cluster_sync_all();   // neither CTA may retire while its peer can still signal or read it
+  } else {
+    __syncthreads();
+  }
   tcgen05_fence_after();
-  if (warp == 2)
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  if (warp == 2) {
+    if constexpr (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
 }
 
 // Exact fp32 re-score of the candidates: the same single fmaf chain, k ascending, as
@@ -240,7 +287,18 @@ __global__ void __launch_bounds__(256) selfjoin_recheck_kernel(const int64_t* __
 
 // ---- host side -------------------------------------------------------------------------------------
 // Fills h_panel_start (n_my_panels + 1 entries) and returns the launch parameters.
-int64_t sjm_plan(int64_t n_rows, int32_t rank, int32_t world, int64_t* h_panel_start, int32_t max_panels,
+// CTA pairs or single CTAs?  Pairs keep the tensor pipe busier (+11-14 % on joins that finish within
+// ~0.1 s), but a long join runs against the board's power cap, where what counts is energy per
+// flop and the single-CTA kernel came out 5 % ahead (same-box A/B on one rank's share of C3:
+// 5.91 s vs 6.20-6.31 s, profiles/r01_selfjoin_ab.log).  So: pairs below ~0.12 s of estimated work.
+bool sjm_pair_mode(int64_t n_rows, int32_t dim, int32_t world) {
+  if (const char* e = getenv("MMRS_SJ_PAIR")) return atoi(e) != 0;
+  const double flops = static_cast<double>(dim) * static_cast<double>(n_rows) * static_cast<double>(n_rows) /
+                       static_cast<double>(world > 0 ? world : 1);
+  return flops < 1.44e14;
+}
+
+int64_t sjm_plan(int64_t n_rows, int32_t rank, int32_t world, bool pair, int64_t* h_panel_start, int32_t max_panels,
                  int32_t* n_my_panels) {
   const int64_t nbi = (n_rows + kSjmBM - 1) / kSjmBM, nbj = (n_rows + kSjmBN - 1) / kSjmBN;
   const int64_t n_panels = (nbj + kSjmPanel - 1) / kSjmPanel;
@@ -252,7 +310,7 @@ int64_t sjm_plan(int64_t n_rows, int32_t rank, int32_t world, int64_t* h_panel_s
     if (ni > nbi) ni = nbi;
     int64_t nj = nbj - pnl * kSjmPanel;
     if (nj > kSjmPanel) nj = kSjmPanel;
-    tiles += (ni + 1) / 2 * nj;   // a CTA pair takes two i-blocks at a time
+    tiles += (pair ? (ni + 1) / 2 : ni) * nj;   // a CTA pair takes two i-blocks at a time
   }
   if (h_panel_start) h_panel_start[m] = tiles;
   *n_my_panels = m;
@@ -265,7 +323,7 @@ int64_t sjm_max_panels(int64_t n_rows) {
 }
 
 cudaError_t launch_selfjoin_mma(const __nv_bfloat16* emb16, int64_t n_rows, int32_t dim, int64_t ld16,
-                                float thr_lo, int32_t rank, int32_t world, const int64_t* d_panel_start,
+                                float thr_lo, int32_t rank, int32_t world, bool pair, const int64_t* d_panel_start,
                                 int32_t n_my_panels, int64_t total_tiles, int64_t* cand, int64_t cand_cap,
                                 unsigned long long* cand_count, int32_t* flags, int sm_count,
                                 cudaStream_t stream) {
@@ -282,26 +340,29 @@ cudaError_t launch_selfjoin_mma(const __nv_bfloat16* emb16, int64_t n_rows, int3
   p.panel_stride = world;
   p.panel_start = d_panel_start;
   p.total_tiles = total_tiles;
+  p.ib_per_tile = pair ? 2 : 1;
   p.cand = cand; p.cand_cap = cand_cap; p.cand_count = cand_count;
   CUtensorMap map_a, map_b;
   if (!make_map(&map_a, emb16, static_cast<uint64_t>(n_rows), static_cast<uint64_t>(dim), static_cast<uint64_t>(ld16), kSjmBM))
     return cudaErrorNotSupported;
-  if (!make_map(&map_b, emb16, static_cast<uint64_t>(n_rows), static_cast<uint64_t>(dim), static_cast<uint64_t>(ld16), kSjmBN / 2))
+  if (!make_map(&map_b, emb16, static_cast<uint64_t>(n_rows), static_cast<uint64_t>(dim), static_cast<uint64_t>(ld16), pair ? kSjmBN / 2 : kSjmBN))
     return cudaErrorNotSupported;
-  const size_t smem = 1024 + static_cast<size_t>(kSjmStages) * kSjmStageBytes + sizeof(SjmShared);
-  cudaError_t e = cudaFuncSetAttribute(selfjoin_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem));
+  const size_t smem = 1024 + sizeof(SjmShared) +
+                      (pair ? static_cast<size_t>(SjmCfg<true>::kStages) * SjmCfg<true>::kStageBytes
+                            : static_cast<size_t>(SjmCfg<false>::kStages) * SjmCfg<false>::kStageBytes);
+  auto kernel = pair ? selfjoin_mma_kernel<true> : selfjoin_mma_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return e;
-  int64_t pairs = sm_count / 2;          // one CTA pair per TPC
-  if (pairs > total_tiles) pairs = total_tiles;
+  int64_t units = pair ? sm_count / 2 : sm_count;          // one CTA (pair) per SM (TPC)
+  if (units > total_tiles) units = total_tiles;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(static_cast<unsigned>(2 * pairs)); cfg.blockDim = dim3(kSjmThreads);
+  cfg.gridDim = dim3(static_cast<unsigned>(pair ? 2 * units : units)); cfg.blockDim = dim3(kSjmThreads);
   cfg.dynamicSmemBytes = smem; cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, selfjoin_mma_kernel, map_a, map_b, p, flags);
+  cfg.attrs = attr; cfg.numAttrs = pair ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, map_a, map_b, p, flags);
 }
 
 cudaError_t launch_selfjoin_recheck(const int64_t* cand, int64_t n_cand, const float* emb, int64_t ld, int32_t dim,

@@ -123,6 +123,21 @@ def test_tc_rank_panels_partition_the_join(mm, oracle):
     assert [tuple(p) for p in got.tolist()] == planted
 
 
+@pytest.mark.parametrize("pair", ["0", "1"])
+def test_tc_single_cta_and_cta_pair_kernels(mm, oracle, monkeypatch, pair):
+    """Both schedules of the tensor-core join (chosen by estimated duration, forced here): single CTAs
+    (M = 128) and CTA pairs (tcgen05.mma.cta_group::2, M = 256); odd i-block counts, rank panels."""
+    from mmrs_b200.dedup import selfjoin_tc_raw, sort_pairs, _device_f32
+    monkeypatch.setenv("MMRS_SJ_PAIR", pair)
+    for n, d, seed in [(4_225, 64, 5), (33_333, 768, 33_333), (70_001, 128, 9)]:     # 4225 = 33 i-blocks + 1 row
+        x, planted = oracle.synthetic_dedup(n, d, dup_frac=0.01, seed=seed)
+        xd = _device_f32(x)
+        got = sort_pairs(selfjoin_tc_raw(xd, 0.95), n).cpu()
+        assert [tuple(p) for p in got.tolist()] == planted
+        parts = [selfjoin_tc_raw(xd, 0.95, r, 3) for r in range(3)]
+        assert [tuple(p) for p in sort_pairs(torch.cat(parts), n).cpu().tolist()] == planted
+
+
 def test_tc_buffers_regrow(mm, oracle):
     x = oracle.synthetic_gallery(3000, 64, seed=1, dtype=torch.float32)
     from mmrs_b200.dedup import selfjoin_tc_raw, sort_pairs, _device_f32

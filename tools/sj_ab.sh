@@ -1,0 +1,10 @@
+#!/bin/bash
+# same-box A/B of the self-join tensor-core kernel variants on one rank's share of C3 (run under gpurun)
+PKG=multi-modal-retrieval-system-image-search-and-data-governance_b200
+cp $PKG/lib/libmmrs_b200.so /tmp/lib_a.so
+run() { cp $2 $PKG/lib/libmmrs_b200.so; echo "variant $1"; timeout 300 python tools/c3_one_rank.py 10000000 0 2>&1 | tail -1; nvidia-smi --query-gpu=clocks.sm,power.draw,temperature.gpu --format=csv,noheader; }
+run A-pair /tmp/lib_a.so
+run B-old tools/_ab/libmmrs_b.so
+run C-single-uniform tools/_ab/libmmrs_c.so
+run A-pair /tmp/lib_a.so
+cp /tmp/lib_a.so $PKG/lib/libmmrs_b200.so
