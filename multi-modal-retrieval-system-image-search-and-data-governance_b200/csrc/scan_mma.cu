@@ -18,7 +18,7 @@
 // Roofline: HBM-bound (N*D*2 bytes per pass) up to Q ~ 200, tensor-bound beyond
 // (SURVEY.md section 8d).
 //
-// PAIR mode (more than 128 queries): the grid is launched as clusters of two CTAs (one TPC) that
+// PAIR mode (more than 64 queries): the grid is launched as clusters of two CTAs (one TPC) that
 // run ONE tcgen05.mma.cta_group::2 of M = 256: each CTA stages its own gallery tile (A, 128 rows)
 // and HALF of the query chunk (B); CTA 0's MMA warp issues for both, each CTA's accumulator
 // (its 128 rows x all queries of the chunk) lands in its own TMEM and is read out by its own
@@ -469,15 +469,19 @@ cudaError_t launch_scan_mma(const ScanParams& p, const __nv_bfloat16* q_bf16, in
   cfg.q_plane_rows = n_q_padded;
   cfg.n_qchunks = n_qchunks;
   cfg.debug_skip_epilogue = getenv("MMRS_K2_DEBUG_SKIP_EPI") ? atoi(getenv("MMRS_K2_DEBUG_SKIP_EPI")) : 0;   // 1: no epilogue, 2: nothing passes
-  // Up to 128 queries the CTA is sized so that TWO fit on an SM (<= 113 KB of shared memory, 80
+  // Up to 64 queries the CTA is sized so that TWO fit on an SM (<= 113 KB of shared memory, 80
   // registers x 384 threads, <= 256 TMEM columns each): the scans of two searches in flight on
   // different streams then share the HBM stream instead of queueing behind each other, and the
   // short seed/mid scans of one search hide under the long last-phase scan of the other.
-  int small_max = 128;   // 33..128 queries: 3-4 ring stages per CTA, two CTAs per SM
+  // (65..128 queries used to run this way too, with only two 32 KB ring stages per CTA; as CTA
+  // pairs they get eight 24 KB stages: 0.216 vs 0.238 ms per step at 128 queries.)
+  int small_max = 64;   // 33..64 queries: 3-4 ring stages per CTA, two CTAs per SM
   if (const char* e = getenv("MMRS_K2_SMALL_MAX")) small_max = atoi(e);
   const bool small = split == 1 && cfg.n_umma <= small_max && getenv("MMRS_K2_BIG_SMEM") == nullptr;
-  // Above that the kernel is tensor-bound and runs as CTA pairs (cta_group::2, see the file header)
-  const bool pair = !small && split == 1 && cfg.n_umma > 128 && getenv("MMRS_K2_NO_PAIR") == nullptr;
+  // Above that the kernel runs as CTA pairs (cta_group::2, see the file header)
+  int pair_min = 64;
+  if (const char* e = getenv("MMRS_K2_PAIR_MIN")) pair_min = atoi(e);
+  const bool pair = !small && split == 1 && cfg.n_umma > pair_min && getenv("MMRS_K2_NO_PAIR") == nullptr;
   if (pair) cfg.n_umma = (cfg.n_umma + 31) / 32 * 32;   // each CTA stages half the query rows
   int cols = 32;
   while (cols < 2 * cfg.n_umma) cols <<= 1;
@@ -536,7 +540,7 @@ cudaError_t launch_scan_mma(const ScanParams& p, const __nv_bfloat16* q_bf16, in
     }
   }
   if (pair) {
-    switch (mode) {   // > 128 queries: tensor-bound, one CTA per SM, CTA pairs, 16 epilogue warps each
+    switch (mode) {   // > 64 queries: one CTA per SM, CTA pairs, 16 epilogue warps each
       case kModeScores: return go(scan_mma_kernel<kModeScores, 16, true>);
       case kModeDense: return go(scan_mma_kernel<kModeDense, 16, true>);
       default: return go(scan_mma_kernel<kModeFilter, 16, true>);

@@ -256,7 +256,9 @@ def test_mma_path_matches_oracle(mm, oracle, n, d, nq, k):
 
 
 @pytest.mark.parametrize("n,d,nq,k", [
-    (70_001, 512, 130, 100),     # UMMA N = 160: each CTA of the pair stages 80 query rows
+    (20_000, 768, 70, 20),       # UMMA N = 96: each CTA of the pair stages 48 query rows
+    (50_000, 512, 96, 100),
+    (70_001, 512, 130, 100),     # N = 160
     (40_000, 768, 200, 50),      # N = 224
     (8_321, 64, 700, 5),         # three query chunks as work units, odd tile count, few tiles
     (33_000, 520, 1024, 10),     # four chunks
@@ -264,7 +266,7 @@ def test_mma_path_matches_oracle(mm, oracle, n, d, nq, k):
     (128, 64, 256, 128),         # one tile: the second CTA of the pair has nothing to read
 ])
 def test_mma_cta_pair_mode_matches_oracle(mm, oracle, n, d, nq, k):
-    """More than 128 queries run as CTA pairs (tcgen05.mma.cta_group::2, M = 256)."""
+    """More than 64 queries run as CTA pairs (tcgen05.mma.cta_group::2, M = 256)."""
     g = oracle.synthetic_gallery(n, d, seed=(n + d) % 89, dtype=torch.bfloat16)
     q = oracle.synthetic_queries(nq, d, seed=nq)
     check_bf16(mm, oracle, g, q, k, "mma")
