@@ -317,6 +317,15 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
       const bool row_ok = row <= last_row;
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                               as * static_cast<uint32_t>(cfg.acc_stride);
+      bool released = false;
+      auto release_accumulator = [&]() {
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (PAIR) mbar_arrive_cluster(tmem_empty_leader + as * 8u);
+          else mbar_arrive(&sh->tmem_empty[as]);
+        }
+      };
       if (!un.valid || (MODE == kModeFilter && cfg.debug_skip_epilogue == 1)) {
         // nothing to read: a duplicate half tile, or mainloop-only timing
       } else if constexpr (MODE == kModeFilter) {
@@ -386,6 +395,12 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
           process16(acc0, c0);
           if (two) process16(acc1, c0 + 16);
         }
+        // the accumulator is read out: hand it back to the MMA warp BEFORE waiting for the slot
+        // atomics of the parked candidates (an L2 round trip that used to sit on the critical path
+        // tmem_full -> read-out -> flush -> tmem_empty: the MMA warp waited for tmem_empty on most
+        // units, profiles/r01_k2_c5like_pair_summary.txt)
+        release_accumulator();
+        released = true;
         if (n_st) flush();
       } else {
       for (int c0 = c_begin; c0 < c_end; c0 += 16) {
@@ -415,12 +430,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
         }
       }
       }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (PAIR) mbar_arrive_cluster(tmem_empty_leader + as * 8u);
-        else mbar_arrive(&sh->tmem_empty[as]);
-      }
+      if (!released) release_accumulator();
       ++it;
     }
   }
