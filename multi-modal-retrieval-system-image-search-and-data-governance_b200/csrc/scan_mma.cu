@@ -22,9 +22,10 @@
 // run ONE tcgen05.mma.cta_group::2 of M = 256: each CTA stages its own gallery tile (A, 128 rows)
 // and HALF of the query chunk (B); CTA 0's MMA warp issues for both, each CTA's accumulator
 // (its 128 rows x all queries of the chunk) lands in its own TMEM and is read out by its own
-// epilogue warps.  With one SM per MMA the tensor pipe idles a third of the time waiting for its
-// shared-memory operands (A + B = 12 KB per 128 clocks; ncu: 66 % duty with the ring always full,
-// profiles/r01_k2_c5like_summary.txt); the pair halves the B traffic per SM.  Work units of a
+// epilogue warps.  The pair halves the query-operand traffic per SM (TMA fill and shared-memory
+// reads: A + B/2 instead of A + B per MMA; L2 -> SM bytes of a C5-shaped scan 35.8 -> 23.9 GB) and
+// makes the ring stages 32 instead of 48 KB; same-box A/B: +11-14 % under the power cap
+// (profiles/r01_pair_ab.log, profiles/r01_k2_c5like*_summary.txt).  Work units of a
 // pair are (tile pair, query chunk) in chunk-minor order, so the chunks of one tile pair are
 // scanned by neighbouring pairs at the same time and share the tile through L2.
 #include <stdlib.h>

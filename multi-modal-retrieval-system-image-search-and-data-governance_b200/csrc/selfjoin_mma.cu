@@ -4,9 +4,9 @@
 // candidate pass runs on the 5th-gen tensor cores over a bf16 copy of the unit-norm embeddings:
 //   S[256 rows i, 256 rows j] = X16[i-blocks] * X16[j-block]^T     (tcgen05.mma.cta_group::2, M=256, N=256)
 // by a PAIR of CTAs (one TPC): each CTA stages its own 128-row i-block and half of the j-block,
-// CTA 0's MMA warp issues for both, each CTA's 128 x 256 accumulator lands in its own TMEM (with one
-// SM per MMA the tensor pipe waits for shared-memory operands a third of the time, see scan_mma.cu);
-// the epilogue keeps pairs (i < j) with S >= tau - margin.  Rounding unit rows to bf16 moves a
+// CTA 0's MMA warp issues for both, each CTA's 128 x 256 accumulator lands in its own TMEM (less
+// operand traffic per SM, see scan_mma.cu); long joins use single CTAs (M=128) instead, see
+// sjm_pair_mode.  The epilogue keeps pairs (i < j) with S >= tau - margin.  Rounding unit rows to bf16 moves a
 // dot product by at most ||a|| ||b - b^|| + ||a - a^|| ||b^|| <= 2 * 2^-9 (1 + 2^-9) < 0.004
 // (Cauchy-Schwarz; round-to-nearest is within 2^-9 relative per element), so with margin >= 0.004
 // every true pair survives; the few survivors are then re-scored in fp32 with exactly the

@@ -92,9 +92,9 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 // ---- CTA pair (cta_group::2): two SMs of one TPC run ONE MMA of M = 256 -----------------------
 // Each CTA stages its own 128 rows of A and HALF of B's rows; the tensor cores of both SMs read
-// the two B halves over the pair link, so the shared-memory operand traffic per SM drops from
-// A + B to A + B/2 per MMA -- with M=128, N=256 per SM that is the difference between 66 % and
-// ~100 % tensor-pipe duty (profiles/r01_k2_c5like_summary.txt).
+// the two B halves over the pair link, so per SM the TMA fill and the shared-memory operand reads
+// drop from A + B to A + B/2 per MMA (L2 -> SM bytes of a C5-shaped scan: 35.8 -> 23.9 GB, ring
+// stages 48 -> 32 KB; profiles/r01_k2_c5like*_summary.txt, same-box A/B in profiles/r01_pair_ab.log).
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
