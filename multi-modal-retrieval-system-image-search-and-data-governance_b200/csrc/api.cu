@@ -146,7 +146,8 @@ constexpr int kSuperChunk = 1024;  // queries sharing one set of candidate lists
 static SearchPlan plan_for(int64_t n_rows, int32_t k, int32_t n_queries) {
   // profiles/r01_tune4.log: seed sample of 32-64 tiles, a mid phase 8x as large, everything else last
   const int ratio_dflt = 3;
-  const int dense_dflt = n_queries <= 48 ? 32 : 64;
+  // 40-48 queries: 0.193 ms per step with 64 seed tiles against 0.200-0.209 with 32; no difference up to 32
+  const int dense_dflt = n_queries <= 32 ? 32 : 64;
   return make_search_plan(n_rows, k, kTileRows, env_int("MMRS_RATIO_LOG2", ratio_dflt),
                           env_int("MMRS_DENSE_TILES", dense_dflt));
 }
