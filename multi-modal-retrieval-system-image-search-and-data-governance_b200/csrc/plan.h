@@ -80,4 +80,31 @@ inline SearchPlan make_search_plan(int64_t n_rows, int32_t k, int32_t tile_rows,
   return pl;
 }
 
+// ---- which tiles a phase launch visits, enumerated densely (used by the CTA-pair scan) --------
+// The tiles of a phase are t = j * inc, j in [0, n_sel), except those with t % exc == 0, i.e.
+// j % R == 0 with R = exc / inc (strides are powers of two, so inc divides exc).
+#ifdef __CUDACC__
+#define MMRS_HD __host__ __device__ __forceinline__
+#else
+#define MMRS_HD inline
+#endif
+MMRS_HD int32_t plan_exclusion_ratio(int32_t inc, int32_t exc) { return exc ? exc / inc : 0; }
+MMRS_HD int32_t plan_n_visited(int32_t n_sel, int32_t R) {
+  return R == 1 ? 0 : (R ? n_sel - (n_sel + R - 1) / R : n_sel);
+}
+// the v-th visited tile's j, v in [0, plan_n_visited)
+MMRS_HD int32_t plan_visited_to_j(int32_t v, int32_t R) { return R ? (v / (R - 1)) * R + v % (R - 1) + 1 : v; }
+
+// Work units of the CTA-pair scan: unit u = (tile pair u / n_chunks, query chunk u % n_chunks);
+// CTA `rank` of the pair takes visited tile 2 * (tile pair) + rank.  An odd tile count leaves the
+// last pair half empty: that CTA repeats its partner's tile and `valid` tells its epilogue to skip it.
+struct PairUnit { int32_t j, chunk; bool valid; };
+MMRS_HD int32_t plan_pair_units(int32_t n_visited, int32_t n_chunks) { return (n_visited + 1) / 2 * n_chunks; }
+MMRS_HD PairUnit plan_pair_unit(int32_t u, int32_t rank, int32_t n_chunks, int32_t n_visited, int32_t R) {
+  const int32_t tp = u / n_chunks;
+  const int32_t v = 2 * tp + rank;
+  const bool valid = v < n_visited;
+  return PairUnit{plan_visited_to_j(valid ? v : 2 * tp, R), u - tp * n_chunks, valid};
+}
+
 }  // namespace mmrs

@@ -30,6 +30,7 @@
 // scanned by neighbouring pairs at the same time and share the tile through L2.
 #include <stdlib.h>
 
+#include "plan.h"
 #include "tcgen05_utils.cuh"
 
 namespace mmrs {
@@ -73,9 +74,6 @@ struct MmaCfg {
   int32_t n_qchunks;     // pair mode: query chunks of kMaxQ in this launch (they are work units, not gridDim.y)
 };
 
-// The tiles of a phase are t = j * inc, j in [0, n_sel), except those with t % exc == 0, i.e.
-// j % R == 0 with R = exc / inc (strides are powers of two, plan.h).  The v-th tile that IS visited:
-__device__ __forceinline__ int valid_to_j(int v, int R) { return R ? (v / (R - 1)) * R + v % (R - 1) + 1 : v; }
 
 
 template <int MODE, int EPI_WARPS, bool PAIR>
@@ -113,19 +111,17 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
   // u % n_qchunks) over the VISITED tiles only; CTA `rank` of the pair takes tile 2 * (tile pair) + rank.
   const int inc = p.sched.tile_inc, exc = p.sched.tile_exc;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
-  const int R = PAIR && exc ? exc / inc : 0;
-  const int n_valid = R == 1 ? 0 : (R ? p.sched.n_sel - (p.sched.n_sel + R - 1) / R : p.sched.n_sel);
+  const int R = PAIR ? plan_exclusion_ratio(inc, exc) : 0;
+  const int n_valid = plan_n_visited(p.sched.n_sel, R);
   const int n_ch = PAIR ? cfg.n_qchunks : 1;
   const int u_begin = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int u_step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
-  const int n_units = PAIR ? (n_valid + 1) / 2 * n_ch : p.sched.n_sel;
+  const int n_units = PAIR ? plan_pair_units(n_valid, n_ch) : p.sched.n_sel;
   struct Unit { int j, chunk; bool valid, skip; };
   auto unit_of = [&](int u) -> Unit {
     if constexpr (PAIR) {
-      const int tp = u / n_ch;
-      const int v = 2 * tp + static_cast<int>(rank);
-      const bool valid = v < n_valid;     // an odd tile count leaves the last pair half empty:
-      return Unit{valid_to_j(valid ? v : 2 * tp, R), u - tp * n_ch, valid, false};   // that CTA repeats its partner's tile, unread
+      const PairUnit pu = plan_pair_unit(u, static_cast<int>(rank), n_ch, n_valid, R);   // plan.h
+      return Unit{pu.j, pu.chunk, pu.valid, false};
     } else {
       return Unit{u, static_cast<int>(blockIdx.y), true, exc != 0 && ((u * inc) % exc) == 0};
     }
@@ -517,13 +513,13 @@ cudaError_t launch_scan_mma(const ScanParams& p, const __nv_bfloat16* q_bf16, in
                 static_cast<uint64_t>(p.ldq), static_cast<uint32_t>(b_rows)))
     return cudaErrorNotSupported;
 
-  const int R = p.sched.tile_exc ? p.sched.tile_exc / p.sched.tile_inc : 0;
-  const int n_valid = R == 1 ? 0 : (R ? p.sched.n_sel - (p.sched.n_sel + R - 1) / R : p.sched.n_sel);
+  const int R = plan_exclusion_ratio(p.sched.tile_inc, p.sched.tile_exc);
+  const int n_valid = plan_n_visited(p.sched.n_sel, R);
   if (n_valid < 1) return cudaSuccess;   // nothing to visit
   dim3 grid;
   if (pair) {
     // one pair per TPC; units = (tile pair, query chunk)
-    const int n_units = (n_valid + 1) / 2 * n_qchunks;
+    const int n_units = plan_pair_units(n_valid, n_qchunks);
     int pairs = sm_count / 2;
     if (pairs > n_units) pairs = n_units;
     grid = dim3(2 * pairs, 1);

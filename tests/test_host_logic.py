@@ -26,6 +26,21 @@ extern "C" int plan(long long n, int k, int ratio, int dense, int* out) {{
   out[0] = p.n_tiles; out[1] = p.n_phases; out[2] = p.dense_rows; out[3] = p.cap;
   for (int i = 0; i < p.n_phases; ++i) {{ out[4+3*i] = p.phase[i].inc; out[5+3*i] = p.phase[i].exc; out[6+3*i] = p.phase[i].n_sel; }}
   return 0;
+}}
+// the visited-tile / CTA-pair work-unit enumeration the scan kernel uses (plan.h)
+extern "C" int visited(int inc, int exc, int n_sel, int* out_j) {{
+  const int R = mmrs::plan_exclusion_ratio(inc, exc), n = mmrs::plan_n_visited(n_sel, R);
+  for (int v = 0; v < n; ++v) out_j[v] = mmrs::plan_visited_to_j(v, R);
+  return n;
+}}
+extern "C" int pair_units(int inc, int exc, int n_sel, int n_chunks, int rank, int* out) {{   // out: [u][j, chunk, valid]
+  const int R = mmrs::plan_exclusion_ratio(inc, exc), n = mmrs::plan_n_visited(n_sel, R);
+  const int units = mmrs::plan_pair_units(n, n_chunks);
+  for (int u = 0; u < units; ++u) {{
+    mmrs::PairUnit pu = mmrs::plan_pair_unit(u, rank, n_chunks, n, R);
+    out[3*u] = pu.j; out[3*u+1] = pu.chunk; out[3*u+2] = pu.valid;
+  }}
+  return units;
 }}''')
     so = d / "shim.so"
     subprocess.run(["g++", "-O1", "-shared", "-fPIC", str(src), "-o", str(so)], check=True)
@@ -61,6 +76,37 @@ def test_plan_visits_every_tile_exactly_once(plan_lib, n, k):
     # later phases: expected appends k * ratio stay far below the capacity
     for (inc_prev, _, _), (inc, _, _) in zip(p["phases"], p["phases"][1:]):
         assert inc_prev % inc == 0 and 4 * (k + 32) * (inc_prev // inc) <= p["cap"]
+
+
+@pytest.mark.parametrize("n", [129, 16385, 70_001, 1_000_000, 12_500_000])
+def test_visited_tiles_and_cta_pair_units(plan_lib, n):
+    """The dense enumeration of a phase's visited tiles, and the (tile pair, query chunk) work units
+    of the CTA-pair scan: every (visited tile, chunk) is read by exactly one CTA."""
+    for dense in (32, 64):
+        p = get_plan(plan_lib, n, 100, dense=dense)
+        for inc, exc, n_sel in p["phases"]:
+            want = [j for j in range(n_sel) if not (exc and (j * inc) % exc == 0)]
+            buf = (ctypes.c_int * max(1, n_sel))()
+            got_n = plan_lib.visited(inc, exc, n_sel, buf)
+            assert got_n == len(want) and list(buf[:got_n]) == want
+            if n_sel > 20_000:
+                continue                      # the unit check below is O(units) in Python
+            for n_chunks in (1, 3, 4):
+                units = (len(want) + 1) // 2 * n_chunks
+                seen = {}
+                for rank in (0, 1):
+                    out = (ctypes.c_int * (3 * max(1, units)))()
+                    assert plan_lib.pair_units(inc, exc, n_sel, n_chunks, rank, out) == units
+                    for u in range(units):
+                        j, chunk, valid = out[3 * u], out[3 * u + 1], out[3 * u + 2]
+                        assert j in want and 0 <= chunk < n_chunks      # even an unread half tile is a real tile
+                        if valid:
+                            assert (j, chunk) not in seen
+                            seen[(j, chunk)] = (u, rank)
+                assert len(seen) == len(want) * n_chunks
+                # the chunks of one tile pair are consecutive units: neighbouring pairs share the tile in L2
+                for (j, chunk), (u, rank) in seen.items():
+                    assert u % n_chunks == chunk and want[2 * (u // n_chunks) + rank] == j
 
 
 def test_shard_bounds(mm):
