@@ -423,8 +423,9 @@ struct GraphKey {
   float scale; int64_t index_offset; int32_t path; float* d_values; int64_t* d_indices;
   void* workspace; int device; int ratio_log2; int dense_tiles; uint64_t* d_keys;
   int32_t g_world, g_rank; const void* g_bufs; const void* g_flags; int64_t g_stride;
+  uint64_t knobs;   // the kernel-shape environment knobs the captured launches were configured with
   bool operator==(const GraphKey& o) const {
-    return g_world == o.g_world && g_rank == o.g_rank && g_bufs == o.g_bufs && g_flags == o.g_flags &&
+    return knobs == o.knobs && g_world == o.g_world && g_rank == o.g_rank && g_bufs == o.g_bufs && g_flags == o.g_flags &&
            g_stride == o.g_stride && d_keys == o.d_keys && gallery == o.gallery && n_rows == o.n_rows && dim == o.dim && ld == o.ld && dtype == o.dtype &&
            d_queries == o.d_queries && n_queries == o.n_queries && ldq_in == o.ldq_in && k == o.k &&
            normalize == o.normalize && scale == o.scale && index_offset == o.index_offset &&
@@ -433,6 +434,19 @@ struct GraphKey {
            dense_tiles == o.dense_tiles;
   }
 };
+// FNV-1a over the values of the MMRS_K2_* / MMRS_NO_PDL knobs (read per launch by the kernels' host
+// side): a graph captured under one setting must not be replayed under another
+static uint64_t knob_hash() {
+  static const char* const kNames[] = {"MMRS_K2_SMALL_MAX", "MMRS_K2_BIG_SMEM", "MMRS_K2_CTAS_PER_SM", "MMRS_K2_QCHUNKS",
+                                       "MMRS_K2_NO_PAIR", "MMRS_K2_PAIR_MIN", "MMRS_K2_DEBUG_SKIP_EPI", "MMRS_NO_PDL"};
+  uint64_t h = 1469598103934665603ull;
+  for (const char* name : kNames) {
+    const char* v = getenv(name);
+    for (const char* c = v ? v : "\x01"; *c; ++c) h = (h ^ static_cast<unsigned char>(*c)) * 1099511628211ull;
+    h = (h ^ 0xffu) * 1099511628211ull;
+  }
+  return h;
+}
 struct GraphEntry { GraphKey key; cudaGraphExec_t exec; uint64_t stamp; long long kernels; };
 static std::mutex g_graph_mu;
 static std::vector<GraphEntry> g_graphs;
@@ -446,7 +460,7 @@ static int launch_search_graph(const SearchArgs& a, const DeviceInfo& dev, const
   GraphKey key{a.gallery, a.n_rows, a.dim, a.ld, a.dtype, a.d_queries, a.n_queries, a.ldq_in, a.k,
                a.normalize, a.scale, a.index_offset, a.path, a.d_values, a.d_indices, workspace,
                dev.device, env_int("MMRS_RATIO_LOG2", -1), env_int("MMRS_DENSE_TILES", -1), a.d_keys,
-               a.g_world, a.g_rank, a.g_peer_bufs, a.g_peer_flags, a.g_list_stride};
+               a.g_world, a.g_rank, a.g_peer_bufs, a.g_peer_flags, a.g_list_stride, knob_hash()};
   cudaGraphExec_t exec = nullptr;
   long long kernels = 0;
   {
