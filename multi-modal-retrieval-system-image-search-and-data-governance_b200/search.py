@@ -355,6 +355,80 @@ def evaluate_thresholds(similarities, thresholds, positive_class, negative_class
     return results
 
 
+def score_classes(image_features, text_features, classes, labels, paths, *, scorer=None):
+    """The similarity loop of the lab pipelines as ONE scoring call: CLIP/lab3.py:108-117,
+    CLIP/union_dataset.py:247-260 (`process_images`, D = 512) and CLIP-Chinese/lab_chinese.py:116-120
+    (D = 768) normalise each image batch (`feats / feats.norm(dim=1, keepdim=True)`) and then, class by
+    class, run `feats @ text_features[cls].t()` followed by a blocking `.cpu()` -- five GEMVs and five
+    syncs per batch of 64.  Here all images of the run and all classes go through one `full_scores`
+    call: the normalised image rows are the gallery (streamed once), the class embeddings the queries.
+
+    image_features [N, D] (as they leave the image tower, NOT yet normalised), text_features
+    {class: [1, D] or [D] unit vector} as built at lab3.py:84-90, `labels` / `paths` the N true labels
+    and file paths.  Returns {class: [{"similarity": float, "true_label": ..., "file_path": ...}, ...]}
+    in image order, items labelled "error" skipped (lab3.py:116) -- exactly what `evaluate_thresholds`
+    and `calc_combined_metrics` consume.  `scorer` is a test hook with the signature of `full_scores`."""
+    classes = list(classes)
+    labels, paths = list(labels), list(paths)
+    feats = image_features if isinstance(image_features, torch.Tensor) else torch.as_tensor(np.asarray(image_features))
+    if feats.dim() != 2 or feats.shape[0] != len(labels) or len(labels) != len(paths):
+        raise ValueError("image_features must be [N, D] with N labels and N paths")
+    out = {cls: [] for cls in classes}
+    if not classes or feats.shape[0] == 0:
+        return out
+    text = torch.stack([torch.as_tensor(text_features[cls]).detach().float().cpu().reshape(-1) for cls in classes])
+    if text.shape[1] != feats.shape[1]:
+        raise ValueError("text and image features differ in width")
+    score = full_scores if scorer is None else scorer
+    feats = feats.detach().float()
+    feats = feats / feats.norm(dim=1, keepdim=True)      # lab3.py:112, at ingest like build_cache (search_image.py:157)
+    sims = score(text, feats, normalize_queries=False, mode="fp32")        # [n_classes, N]; text rows are unit (lab3.py:90)
+    sims = sims.cpu().numpy()
+    keep = [i for i, lab in enumerate(labels) if lab != "error"]
+    for c, cls in enumerate(classes):
+        col = sims[c]
+        out[cls] = [{"similarity": float(col[i]), "true_label": labels[i], "file_path": paths[i]} for i in keep]
+    return out
+
+
+def calc_combined_metrics(en_sims, cn_sims, en_threshs, cn_threshs, en_pos, en_neg, cn_pos, cn_neg, verbose=False):
+    """Drop-in for `calc_combined_metrics` of CLIP/union_dataset.py:133-231: per class pair, an image
+    (keyed by file basename) counts as detected when the English OR the Chinese model scores it at or
+    above that model's threshold; TP over the union of both models' positive-class images, FP over
+    the union of the negative-class images.  Same argument order and result dicts; the reference's
+    debug prints are behind `verbose`.  Basenames repeated inside one model's list: the last item
+    wins, as the reference's dict assignments do."""
+    results = []
+    for i, en_pos_cls in enumerate(en_pos):
+        cn_pos_cls, en_neg_cls, cn_neg_cls = cn_pos[i], en_neg[i], cn_neg[i]
+        en_thresh, cn_thresh = en_threshs[i], cn_threshs[i]
+
+        def flags(items, label, thresh):
+            return {os.path.basename(it["file_path"]): it["similarity"] >= thresh
+                    for it in items if it["true_label"] == label}
+
+        en_p, en_n = flags(en_sims[en_pos_cls], en_pos_cls, en_thresh), flags(en_sims[en_pos_cls], en_neg_cls, en_thresh)
+        cn_p, cn_n = flags(cn_sims[cn_pos_cls], cn_pos_cls, cn_thresh), flags(cn_sims[cn_pos_cls], cn_neg_cls, cn_thresh)
+        pos_names, neg_names = en_p.keys() | cn_p.keys(), en_n.keys() | cn_n.keys()
+        tp = sum(1 for b in pos_names if en_p.get(b, False) or cn_p.get(b, False))
+        fp = sum(1 for b in neg_names if en_n.get(b, False) or cn_n.get(b, False))
+        total_pos, total_neg = len(pos_names), len(neg_names)
+        fn = total_pos - tp
+        prec = tp / (tp + fp) if (tp + fp) > 0 else 0
+        rec = tp / (tp + fn) if (tp + fn) > 0 else 0
+        f1 = 2 * prec * rec / (prec + rec) if (prec + rec) > 0 else 0
+        if verbose:
+            print(f"{en_pos_cls} vs {en_neg_cls}: unique pos {total_pos}, unique neg {total_neg}, "
+                  f"TP {tp}, FP {fp}, FN {fn}, precision {prec:.3f}, recall {rec:.3f}, F1 {f1:.3f}")
+        results.append({"en_positive_class": en_pos_cls, "en_negative_class": en_neg_cls,
+                        "cn_positive_class": cn_pos_cls, "cn_negative_class": cn_neg_cls,
+                        "en_threshold": en_thresh, "cn_threshold": cn_thresh,
+                        "combined_f1": f1, "combined_precision": prec, "combined_recall": rec,
+                        "TP": tp, "FP": fp, "FN": fn,
+                        "total_unique_pos": total_pos, "total_unique_neg": total_neg})
+    return results
+
+
 def eval_threshold(pos_res, neg_res, threshold):
     """Drop-in for code/search_image.py:39-56 -> (f1_score, precision, recall)."""
     tp, fp = threshold_sweep_counts(pos_res, neg_res, [threshold])

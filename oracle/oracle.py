@@ -205,6 +205,25 @@ def lab_evaluate_thresholds(similarities, thresholds, positive_class, negative_c
 # near-duplicate self-join (BASELINE.json north_star):
 #   triu((G @ G.T) >= tau, 1).nonzero()   -- row-major nonzero == lexicographic (i, j)
 # --------------------------------------------------------------------------------------------
+def lab_process_images(image_features: torch.Tensor, text_features: dict, classes, labels, paths, batch: int = 64):
+    """The similarity loop of CLIP/union_dataset.py:247-260 (`process_images`; the same lines are
+    CLIP/lab3.py:108-117 and CLIP-Chinese/lab_chinese.py:116-120) on features that have already left
+    the image tower: per batch of `batch` images (lab3.py:73) normalise the rows
+    (`feats / feats.norm(dim=1, keepdim=True)`), then class by class `feats @ text_features[cls].t()`;
+    items whose label is "error" are skipped.  Same batching as the reference, so the fp32 CPU
+    results are bit-identical to the recorded golden."""
+    out = {cls: [] for cls in classes}
+    for lo in range(0, image_features.shape[0], batch):
+        feats = image_features[lo:lo + batch].float()
+        feats = feats / feats.norm(dim=1, keepdim=True)
+        for cls in classes:
+            sims = (feats @ text_features[cls].t()).squeeze().cpu().numpy()
+            for s, lab, p in zip(np.atleast_1d(sims), labels[lo:lo + batch], paths[lo:lo + batch]):
+                if lab != "error":
+                    out[cls].append({"similarity": float(s), "true_label": lab, "file_path": p})
+    return out
+
+
 def dedup_pairs(emb: torch.Tensor, threshold: float, block: int = 4096) -> torch.Tensor:
     g = _gallery_f32(emb)
     n = g.shape[0]

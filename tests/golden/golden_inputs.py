@@ -83,3 +83,37 @@ def lab3_inputs():
                     for i, (s, l) in enumerate(zip(sim, lab))]
     thresholds = np.linspace(0.0, 0.5, 1001)
     return similarities, thresholds, "dog", "others"
+
+
+def union_inputs():
+    """Inputs for CLIP/union_dataset.py process_images (:247-260) and calc_combined_metrics (:133-231):
+    two "models" (EN D=512, CN D=768) over overlapping sets of files.  Returns a dict with, per model,
+    un-normalised image features [N, D], unit text features {class: [1, D]}, labels, paths (some label
+    "error", some basenames shared between the models, one basename repeated inside a model), plus
+    class lists and per-pair thresholds."""
+    g = torch.Generator().manual_seed(33)
+    en_pos, en_neg = ["dog", "cat"], ["wolf", "lynx"]
+    cn_pos, cn_neg = ["gou", "mao"], ["lang", "shelizi"]
+
+    def model(d, pos, neg, n, prefix, shift):
+        classes = pos + neg + ["other"]
+        lab_idx = torch.randint(0, len(classes), (n,), generator=g)
+        centers = torch.randn(len(classes), d, generator=g)
+        feats = centers[lab_idx] * 0.12 + torch.randn(n, d, generator=g)          # weak signal: both outcomes on both sides of the thresholds
+        feats = feats * (0.5 + torch.rand(n, 1, generator=g))             # NOT unit norm
+        labels = [classes[int(i)] for i in lab_idx]
+        for i in range(0, n, 17):
+            labels[i] = "error"                                              # unreadable image (lab3.py:116)
+        paths = [f"/data/{prefix}/{labels[i]}/img_{(i + shift) % (n + 5)}.jpg" for i in range(n)]
+        paths[5] = paths[3]                                                  # a basename twice inside one model
+        text = {}
+        for c, cls in enumerate(pos):
+            t = centers[c] + 0.3 * torch.randn(d, generator=g)
+            text[cls] = (t / t.norm()).reshape(1, d)
+        return feats.contiguous(), text, labels, paths
+
+    en = model(512, en_pos, en_neg, 150, "en", 0)
+    cn = model(768, cn_pos, cn_neg, 140, "cn", 3)
+    # make the CN label names line up with the EN file basenames class-wise: same index -> same kind
+    return dict(en=en, cn=cn, en_pos=en_pos, en_neg=en_neg, cn_pos=cn_pos, cn_neg=cn_neg,
+                en_threshs=[0.10, 0.09], cn_threshs=[0.095, 0.11])

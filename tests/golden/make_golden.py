@@ -10,6 +10,8 @@ their inputs' seeds and their OUTPUTS are stored (tests/golden/*.npz, *.json).
   code/search_image.py   get_similarity (:105-117), eval_threshold (:39-56), find_thresholds (:58-103)
   code/utils.py          cls_acc (:15-39)  -> the only topk in the repo (:17)
   CLIP/lab3.py           evaluate_thresholds (:39-65)
+  CLIP/union_dataset.py  process_images (:247-260, fed a stand-in "model" whose image tower returns
+                         the seeded feature batches), calc_combined_metrics (:133-231)
   tool/find_repeated.py  calculate_image_hash (:6-19), get_all_images (:21-33),
                          find_and_remove_duplicate_images (:35-71)
 
@@ -31,7 +33,7 @@ import torch
 
 HERE = Path(__file__).resolve().parent
 sys.path.insert(0, str(HERE))
-from golden_inputs import (dedup_image_set, lab3_inputs, similarity_inputs, topk_inputs)  # noqa: E402
+from golden_inputs import (dedup_image_set, lab3_inputs, similarity_inputs, topk_inputs, union_inputs)  # noqa: E402
 
 
 def extract_functions(path: Path, names: list[str], namespace: dict) -> dict:
@@ -86,6 +88,34 @@ def main(ref_root: str) -> None:
     res = ns4["evaluate_thresholds"](sims, thresholds, pos_cls, neg_cls)
     keys = ["threshold", "precision", "recall", "f1", "TP", "FP", "TN", "FN"]
     np.savez(HERE / "lab3_golden.npz", **{k: np.array([r[k] for r in res], dtype=np.float64) for k in keys})
+
+    # ---- CLIP/union_dataset.py process_images (:247-260) + calc_combined_metrics (:133-231) ------------
+    import contextlib, io
+    ns5 = {"os": os, "torch": torch, "tqdm": lambda it, **kw: it}
+    extract_functions(ref / "CLIP" / "union_dataset.py", ["process_images", "calc_combined_metrics"], ns5)
+    u = union_inputs()
+
+    class FeatureTower:                      # stands in for the CLIP models: the "images" ARE the features
+        def encode_image(self, imgs):        # model_type == "en" (:251)
+            return imgs
+        def get_image_features(self, pixel_values):   # model_type == "cn" (:252)
+            return pixel_values
+
+    def loader(feats, labels, paths, batch=64):       # what the DataLoader yields: (imgs, labels, paths)
+        for lo in range(0, feats.shape[0], batch):
+            yield feats[lo:lo + batch], labels[lo:lo + batch], paths[lo:lo + batch]
+
+    sims = {}
+    for key, pos in (("en", u["en_pos"]), ("cn", u["cn_pos"])):
+        feats, text, labels, paths = u[key]
+        sims[key] = ns5["process_images"](loader(feats, labels, paths), FeatureTower(), text, pos, "cpu", model_type=key)
+    with contextlib.redirect_stdout(io.StringIO()):   # the reference prints debug lines
+        combined = ns5["calc_combined_metrics"](sims["en"], sims["cn"], u["en_threshs"], u["cn_threshs"],
+                                                u["en_pos"], u["en_neg"], u["cn_pos"], u["cn_neg"])
+    (HERE / "union_golden.json").write_text(json.dumps(
+        {"sims": {k: {cls: [[it["similarity"], it["true_label"], it["file_path"]] for it in v] for cls, v in d.items()}
+                  for k, d in sims.items()},
+         "combined": combined}, indent=0, sort_keys=True))
 
     # ---- tool/find_repeated.py --------------------------------------------------------------
     import hashlib

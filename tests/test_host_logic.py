@@ -178,3 +178,40 @@ def test_query_construction_helpers(mm, oracle):
     assert abs(float(got.norm()) - 1.0) > 1e-3     # un-normalised, as in the reference (M3)
     text = torch.from_numpy(rng.standard_normal(64).astype(np.float32))
     assert torch.equal(mm.mix_image_text_query(got, text), (want + text) / 2)
+
+
+def _union_gold():
+    import json
+    from conftest import GOLDEN
+    g = json.loads((GOLDEN / "union_golden.json").read_text())
+    sims = {k: {cls: [{"similarity": a, "true_label": b, "file_path": c} for a, b, c in v] for cls, v in d.items()}
+            for k, d in g["sims"].items()}
+    return sims, g["combined"]
+
+
+def test_calc_combined_metrics_matches_reference(mm):
+    """CLIP/union_dataset.py:133-231, golden recorded from the reference function."""
+    from golden_inputs import union_inputs
+    u = union_inputs()
+    sims, want = _union_gold()
+    got = mm.calc_combined_metrics(sims["en"], sims["cn"], u["en_threshs"], u["cn_threshs"],
+                                   u["en_pos"], u["en_neg"], u["cn_pos"], u["cn_neg"])
+    assert got == want
+    assert all(r["TP"] > 0 and r["FN"] > 0 for r in want) and any(r["FP"] > 0 for r in want)   # a non-trivial fixture
+
+
+def test_score_classes_host_logic(mm, oracle):
+    """score_classes = the per-class loop of the lab scripts as one scoring call; here the scoring call
+    is the oracle's, so this pins the normalisation, the class/row bookkeeping and the "error" filter."""
+    from golden_inputs import union_inputs
+    u = union_inputs()
+    sims, _ = _union_gold()
+    for key, pos in (("en", u["en_pos"]), ("cn", u["cn_pos"])):
+        feats, text, labels, paths = u[key]
+        got = mm.score_classes(feats, text, pos, labels, paths, scorer=lambda q, g, **kw: oracle.full_scores(q, g, **kw))
+        assert list(got) == pos
+        for cls in pos:
+            want = sims[key][cls]
+            assert [(it["true_label"], it["file_path"]) for it in got[cls]] == [(it["true_label"], it["file_path"]) for it in want]
+            np.testing.assert_allclose([it["similarity"] for it in got[cls]], [it["similarity"] for it in want], atol=1e-6, rtol=0)
+    assert mm.score_classes(torch.zeros(0, 8), {}, [], [], []) == {}

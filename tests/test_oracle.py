@@ -132,3 +132,15 @@ def test_lab3_evaluate_thresholds_matches_reference(oracle):
     res = oracle.lab_evaluate_thresholds(sims, thresholds, pos_cls, neg_cls)
     for key in ("threshold", "precision", "recall", "f1", "TP", "FP", "TN", "FN"):
         np.testing.assert_array_equal(np.array([r[key] for r in res], dtype=np.float64), g[key])
+
+
+def test_lab_process_images_matches_reference(oracle):
+    """CLIP/union_dataset.py process_images, run by make_golden.py on seeded feature batches."""
+    from golden_inputs import union_inputs
+    gold = json.loads((GOLDEN / "union_golden.json").read_text())["sims"]
+    u = union_inputs()
+    for key, pos in (("en", u["en_pos"]), ("cn", u["cn_pos"])):
+        feats, text, labels, paths = u[key]
+        got = oracle.lab_process_images(feats, text, pos, labels, paths)
+        for cls in pos:
+            assert [[it["similarity"], it["true_label"], it["file_path"]] for it in got[cls]] == gold[key][cls]

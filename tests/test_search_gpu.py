@@ -442,3 +442,27 @@ def test_lab3_evaluate_thresholds_golden(mm):
         np.testing.assert_array_equal(np.array([r[key] for r in res], dtype=np.float64), g[key])
     best = max(res, key=lambda x: x["f1"])              # lab3.py:123
     assert best["f1"] == g["f1"].max()
+
+
+def test_score_classes_and_union_metrics_golden(mm):
+    """CLIP/union_dataset.py process_images (:247-260) + calc_combined_metrics (:133-231): all images x
+    all classes in one GPU scoring call (D = 512 and D = 768) against the outputs recorded from the
+    reference functions; the EN-or-CN union metrics computed from the GPU scores equal the recorded ones."""
+    import json
+    from golden_inputs import union_inputs
+    g = json.loads((GOLDEN / "union_golden.json").read_text())
+    u = union_inputs()
+    sims = {}
+    for key, pos, threshs in (("en", u["en_pos"], u["en_threshs"]), ("cn", u["cn_pos"], u["cn_threshs"])):
+        feats, text, labels, paths = u[key]
+        sims[key] = mm.score_classes(feats, text, pos, labels, paths)
+        for cls, th in zip(pos, threshs):
+            want = g["sims"][key][cls]
+            got = sims[key][cls]
+            assert [[it["true_label"], it["file_path"]] for it in got] == [w[1:] for w in want]
+            w = np.array([x[0] for x in want])
+            np.testing.assert_allclose([it["similarity"] for it in got], w, atol=1e-5, rtol=0)
+            assert np.abs(w - th).min() > 1e-5          # no recorded score sits on its threshold
+    got = mm.calc_combined_metrics(sims["en"], sims["cn"], u["en_threshs"], u["cn_threshs"],
+                                   u["en_pos"], u["en_neg"], u["cn_pos"], u["cn_neg"])
+    assert got == g["combined"]
