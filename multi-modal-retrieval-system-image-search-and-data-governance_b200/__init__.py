@@ -13,6 +13,7 @@ functions for this path (same names, positional order and return tuples):
     CLIP/lab3.py (and lab_chinese.py, union_dataset.py)
                            evaluate_thresholds, score_classes (the per-class similarity loop as one call)
     CLIP/union_dataset.py  calc_combined_metrics
+    code/main_custom.py    find_thresholds(..., grid="overlap") (:46-91), get_similarity_from_matrix (:93-105)
 
 plus the tensor-level entry points they sit on: search_topk, full_scores, find_duplicate_pairs,
 DeviceGallery, ShardedGallery.  Everything computes through the C-ABI CUDA library
@@ -21,7 +22,7 @@ DeviceGallery, ShardedGallery.  Everything computes through the C-ABI CUDA libra
 from . import _cabi  # noqa: F401  (fails loudly when the CUDA library is missing)
 from .gallery import DeviceGallery, load_feature_cache
 from .search import (best_threshold_on_device, calc_combined_metrics, construct_dataset, eval_threshold, evaluate_thresholds, find_thresholds, full_scores,
-                     get_similarity, mix_image_text_query, outlier_filter_features, score_classes, search_topk,
+                     get_similarity, get_similarity_from_matrix, mix_image_text_query, outlier_filter_features, score_classes, search_topk,
                      threshold_sweep_counts)
 from .dedup import (detect_and_remove_cross_set_duplicates, find_and_remove_duplicate_images, find_duplicate_pairs,
                     find_and_remove_near_duplicate_images, get_all_images, greedy_first_keeper)
@@ -31,7 +32,7 @@ __all__ = [
     "DeviceGallery", "ShardedGallery", "best_threshold_on_device", "calc_combined_metrics", "construct_dataset",
     "detect_and_remove_cross_set_duplicates", "evaluate_thresholds", "eval_threshold", "find_thresholds",
     "find_and_remove_duplicate_images", "find_and_remove_near_duplicate_images",
-    "find_duplicate_pairs", "full_scores", "get_all_images", "get_similarity",
+    "find_duplicate_pairs", "full_scores", "get_all_images", "get_similarity", "get_similarity_from_matrix",
     "greedy_first_keeper", "load_feature_cache", "mix_image_text_query", "outlier_filter_features",
     "score_classes", "search_topk", "shard_bounds",
     "threshold_sweep_counts",

@@ -216,6 +216,16 @@ def get_similarity(features, targets, label, ref_feature, device="cuda"):
         return scores[pos_mask], scores[neg_mask]
 
 
+def get_similarity_from_matrix(similarity, targets, label, device="cuda"):
+    """Drop-in for the OTHER `get_similarity` of the reference, code/main_custom.py:93-105: the scores of
+    class `label` are a column of an already computed [N, classes] similarity matrix (e.g.
+    `full_scores(class_embeddings, gallery).T`); returns (pos_res, neg_res) split by `targets == label`."""
+    scores = similarity[:, label]
+    scores = scores.detach().cpu().numpy() if isinstance(scores, torch.Tensor) else np.asarray(scores)
+    t = targets.detach().cpu().numpy() if isinstance(targets, torch.Tensor) else np.asarray(targets)
+    return scores[t == label], scores[t != label]
+
+
 def construct_dataset(feature_dict, sample_images, class_name):
     """Drop-in for code/search_image.py:167-182: gallery of every cached image except the
     `sample_images` of `class_name`; returns `(test_features [N, D] tensor, targets np.ndarray)`.
@@ -436,17 +446,30 @@ def eval_threshold(pos_res, neg_res, threshold):
     return f1[0], p[0], r[0]
 
 
-def find_thresholds(pos_res, neg_res, target_class, verbose=False):
+def find_thresholds(pos_res, neg_res, target_class, verbose=False, grid="full"):
     """Drop-in for code/search_image.py:58-103: 200-point linspace over [min, max] of all scores,
     F1 per threshold, FIRST strict maximum wins (:74); returns best_f1_score.  The O(200 * N)
-    interpreted `sum(pos_res >= threshold)` loops run as one histogram pass on the GPU."""
+    interpreted `sum(pos_res >= threshold)` loops run as one histogram pass on the GPU.
+    grid="overlap" is the variant of code/main_custom.py:46-50: the grid spans only the range where
+    positive and negative scores overlap, [max(min pos, min neg), min(max pos, max neg)], with
+    int(10 * width) points (none at all when the classes overlap over less than 0.1)."""
     pos_np = np.asarray(pos_res)
     neg_np = np.asarray(neg_res)
-    min_val = min(pos_np.min(), neg_np.min())
-    max_val = max(pos_np.max(), neg_np.max())
-    thresholds = np.linspace(min_val, max_val, 200)
-    tp, fp = threshold_sweep_counts(pos_np, neg_np, thresholds)
-    f1s, ps, rs = _f1_from_counts(tp, fp, int(pos_np.size))
+    if grid == "full":
+        min_val = min(pos_np.min(), neg_np.min())
+        max_val = max(pos_np.max(), neg_np.max())
+        thresholds = np.linspace(min_val, max_val, 200)
+    elif grid == "overlap":
+        min_val = max(pos_np.min(), neg_np.min())
+        max_val = min(pos_np.max(), neg_np.max())
+        thresholds = np.linspace(min_val, max_val, int((max_val - min_val) * 10))
+    else:
+        raise ValueError("grid must be 'full' (search_image.py) or 'overlap' (main_custom.py)")
+    if thresholds.size:
+        tp, fp = threshold_sweep_counts(pos_np, neg_np, thresholds)
+        f1s, ps, rs = _f1_from_counts(tp, fp, int(pos_np.size))
+    else:
+        f1s = ps = rs = np.zeros(0)
 
     best_threshold = 0.
     best_f1_score = 0.

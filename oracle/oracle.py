@@ -164,12 +164,18 @@ def eval_threshold(pos_res, neg_res, threshold):
     return f1_score, precision, recall
 
 
-def find_thresholds(pos_res, neg_res, n_points: int = 200):
+def find_thresholds(pos_res, neg_res, n_points: int = 200, grid: str = "full"):
     """Returns (best_f1, best_threshold, best_precision, best_recall, thresholds, f1_scores);
-    the reference returns best_f1 only (:103) and prints the rest."""
-    min_val = min(min(pos_res), min(neg_res))
-    max_val = max(max(pos_res), max(neg_res))
-    thresholds = np.linspace(min_val, max_val, n_points)
+    the reference returns best_f1 only (:103) and prints the rest.  grid="overlap": the grid of
+    code/main_custom.py:46-50 (overlap range of the two score sets, int(10 * width) points)."""
+    if grid == "overlap":
+        min_val = max(min(pos_res), min(neg_res))
+        max_val = min(max(pos_res), max(neg_res))
+        thresholds = np.linspace(min_val, max_val, int((max_val - min_val) * 10))
+    else:
+        min_val = min(min(pos_res), min(neg_res))
+        max_val = max(max(pos_res), max(neg_res))
+        thresholds = np.linspace(min_val, max_val, n_points)
     best = (0., 0., 0., 0.)
     f1s = []
     for t in thresholds:

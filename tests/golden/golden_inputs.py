@@ -117,3 +117,16 @@ def union_inputs():
     # make the CN label names line up with the EN file basenames class-wise: same index -> same kind
     return dict(en=en, cn=cn, en_pos=en_pos, en_neg=en_neg, cn_pos=cn_pos, cn_neg=cn_neg,
                 en_threshs=[0.10, 0.09], cn_threshs=[0.095, 0.11])
+
+
+def overlap_grid_inputs() -> dict:
+    """name -> (pos_res, neg_res) fp32 score sets for code/main_custom.py find_thresholds (:46-91), whose grid
+    spans the OVERLAP of the two sets: two overlapping pairs, one overlapping over less than 0.1 (zero
+    grid points) and one separable pair (negative width: numpy raises inside the reference)."""
+    rng = np.random.default_rng(17)
+    return {
+        "wide": ((25 + 5 * rng.standard_normal(400)).astype(np.float32), (15 + 5 * rng.standard_normal(3000)).astype(np.float32)),
+        "skewed": ((22 + 2 * rng.standard_normal(50)).astype(np.float32), (20 + 3 * rng.standard_normal(20000)).astype(np.float32)),
+        "narrow": (np.array([0.50, 0.53], dtype=np.float32), np.array([0.48, 0.52], dtype=np.float32)),
+        "separable": (np.array([30.0, 31.0, 35.0], dtype=np.float32), np.array([10.0, 12.0, 29.0], dtype=np.float32)),
+    }

@@ -9,6 +9,8 @@ their inputs' seeds and their OUTPUTS are stored (tests/golden/*.npz, *.json).
 
   code/search_image.py   get_similarity (:105-117), eval_threshold (:39-56), find_thresholds (:58-103)
   code/utils.py          cls_acc (:15-39)  -> the only topk in the repo (:17)
+  code/main_custom.py    eval_threshold (:27-45), find_thresholds (:46-91: the overlap-range grid),
+                         get_similarity (:93-105: column slice of a similarity matrix)
   CLIP/lab3.py           evaluate_thresholds (:39-65)
   CLIP/union_dataset.py  process_images (:247-260, fed a stand-in "model" whose image tower returns
                          the seeded feature batches), calc_combined_metrics (:133-231)
@@ -33,7 +35,8 @@ import torch
 
 HERE = Path(__file__).resolve().parent
 sys.path.insert(0, str(HERE))
-from golden_inputs import (dedup_image_set, lab3_inputs, similarity_inputs, topk_inputs, union_inputs)  # noqa: E402
+from golden_inputs import (dedup_image_set, lab3_inputs, overlap_grid_inputs, similarity_inputs, topk_inputs,  # noqa: E402
+                           union_inputs)
 
 
 def extract_functions(path: Path, names: list[str], namespace: dict) -> dict:
@@ -68,6 +71,24 @@ def main(ref_root: str) -> None:
         out[f"{name}_eval"] = ev
         out[f"{name}_best_f1"] = np.float64(best_f1)
     np.savez(HERE / "search_image_golden.npz", **out)
+
+    # ---- main_custom.py: the other threshold grid (:46-50) and its get_similarity (:93-105) -------------
+    ns6 = {"np": np, "torch": torch}
+    extract_functions(ref / "code" / "main_custom.py", ["eval_threshold", "find_thresholds", "get_similarity"], ns6)
+    out6 = {}
+    for name, (pos, neg) in overlap_grid_inputs().items():
+        try:
+            with np.errstate(all="ignore"):
+                out6[f"{name}_best_f1"] = np.float64(ns6["find_thresholds"](pos, neg, "golden", verbose=False))
+            out6[f"{name}_raises"] = np.array("")
+        except Exception as e:                                   # separable sets: negative sample count (:49-50)
+            out6[f"{name}_best_f1"] = np.float64("nan")
+            out6[f"{name}_raises"] = np.array(type(e).__name__)
+    feats, targets, label, _ = similarity_inputs()["small"]
+    sim = 100.0 * feats @ feats[:7].t()                          # a [N, classes] similarity matrix as main_custom builds it
+    p6, n6 = ns6["get_similarity"](sim, torch.from_numpy(targets), label)
+    out6["sliced_pos"], out6["sliced_neg"] = p6, n6
+    np.savez(HERE / "main_custom_golden.npz", **out6)
 
     # ---- utils.py cls_acc / topk ----------------------------------------------------------
     ns2 = {"torch": torch}

@@ -215,3 +215,17 @@ def test_score_classes_host_logic(mm, oracle):
             assert [(it["true_label"], it["file_path"]) for it in got[cls]] == [(it["true_label"], it["file_path"]) for it in want]
             np.testing.assert_allclose([it["similarity"] for it in got[cls]], [it["similarity"] for it in want], atol=1e-6, rtol=0)
     assert mm.score_classes(torch.zeros(0, 8), {}, [], [], []) == {}
+
+
+def test_get_similarity_from_matrix_matches_reference(mm):
+    """code/main_custom.py:93-105 (column slice of a similarity matrix), golden from the reference function."""
+    from conftest import GOLDEN
+    from golden_inputs import similarity_inputs
+    g = np.load(GOLDEN / "main_custom_golden.npz")
+    feats, targets, label, _ = similarity_inputs()["small"]
+    sim = 100.0 * feats @ feats[:7].t()
+    pos, neg = mm.get_similarity_from_matrix(sim, torch.from_numpy(targets), label)
+    np.testing.assert_array_equal(pos, g["sliced_pos"])
+    np.testing.assert_array_equal(neg, g["sliced_neg"])
+    pos2, neg2 = mm.get_similarity_from_matrix(sim.numpy(), targets, label)
+    np.testing.assert_array_equal(pos2, pos) and np.testing.assert_array_equal(neg2, neg)

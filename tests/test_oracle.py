@@ -144,3 +144,15 @@ def test_lab_process_images_matches_reference(oracle):
         got = oracle.lab_process_images(feats, text, pos, labels, paths)
         for cls in pos:
             assert [[it["similarity"], it["true_label"], it["file_path"]] for it in got[cls]] == gold[key][cls]
+
+
+def test_overlap_grid_find_thresholds_matches_reference(oracle):
+    """code/main_custom.py:46-91: the grid spans only the overlap of the two score sets."""
+    from golden_inputs import overlap_grid_inputs
+    g = np.load(GOLDEN / "main_custom_golden.npz")
+    for name, (pos, neg) in overlap_grid_inputs().items():
+        if str(g[f"{name}_raises"]):
+            with pytest.raises(ValueError):
+                oracle.find_thresholds(pos, neg, grid="overlap")
+        else:
+            assert oracle.find_thresholds(pos, neg, grid="overlap")[0] == g[f"{name}_best_f1"]

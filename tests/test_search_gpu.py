@@ -466,3 +466,15 @@ def test_score_classes_and_union_metrics_golden(mm):
     got = mm.calc_combined_metrics(sims["en"], sims["cn"], u["en_threshs"], u["cn_threshs"],
                                    u["en_pos"], u["en_neg"], u["cn_pos"], u["cn_neg"])
     assert got == g["combined"]
+
+
+def test_overlap_grid_find_thresholds_golden(mm):
+    """find_thresholds(grid="overlap") = code/main_custom.py:46-91 on the GPU sweep; golden from the reference."""
+    from golden_inputs import overlap_grid_inputs
+    g = np.load(GOLDEN / "main_custom_golden.npz")
+    for name, (pos, neg) in overlap_grid_inputs().items():
+        if str(g[f"{name}_raises"]):
+            with pytest.raises(ValueError):
+                mm.find_thresholds(pos, neg, name, grid="overlap")
+        else:
+            assert mm.find_thresholds(pos, neg, name, grid="overlap") == g[f"{name}_best_f1"]
