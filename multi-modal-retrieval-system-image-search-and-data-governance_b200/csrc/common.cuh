@@ -18,6 +18,7 @@ constexpr int kFlagOverflow = 1;      // a candidate list outgrew its capacity
 constexpr int kFlagZeroNorm = 2;      // normalize_queries and ||q|| == 0
 constexpr int kFlagShort = 4;         // fewer than k candidates reached a select (bug guard)
 constexpr int kFlagWatchdog = 8;      // an mbarrier wait timed out (K2 debug guard)
+constexpr int kFlagGatherTimeout = 16;  // fused all-gather: a peer rank's flag did not arrive in time
 
 // ---- order-preserving (score, row) -> u64 key ---------------------------------------------
 // Larger key == better match: higher score first, then LOWER row index.  Keys are unique
@@ -97,6 +98,39 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return launch_pdl_cluster(kernel, grid, block, smem, stream, 1u, static_cast<Args&&>(args)...);
 }
 
+// ---- flags exchanged between GPUs (system scope) ----------------------------------------------------
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// Wait until flags[i] >= want for every i in [0, n).  Bounded by wall time: a peer that never
+// arrives (a dead rank) must end this kernel with a status flag, not hang the GPU.  A peer that is
+// merely late is waited for -- no rank can decide on its own to drop the batch (the others would
+// not know), so the bound is generous (MMRS_GATHER_TIMEOUT_MS, default 20 s).
+__device__ __forceinline__ void wait_all_ge(const uint32_t* flags, int n, uint32_t want, int32_t* status,
+                                            uint64_t timeout_ns) {
+  const uint64_t t0 = global_timer_ns();
+  for (int i = 0; i < n; ++i) {
+    uint32_t spins = 0;
+    while (static_cast<int32_t>(ld_acquire_sys(flags + i) - want) < 0) {
+      if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > timeout_ns) {
+        atomicOr(status, kFlagGatherTimeout);
+        return;
+      }
+      __nanosleep(64);
+    }
+  }
+}
+
 // ---- epilogue modes of the scan kernels ---------------------------------------------------
 enum ScanMode : int {
   kModeScores = 0,  // write fp32 scores to out[q, row]                  (full_scores)
@@ -160,13 +194,30 @@ struct SelectParams {
   int32_t g_status_index;          // element of a list that carries the rank's status word
   const uint32_t* g_epoch;         // device: sequence number of this call on this slot (starts at 1)
   uint32_t* g_counter;             // device: CTAs done (returns to 0)
+  uint32_t* g_status_out;          // consumer: [g_world] private snapshot of the ranks' status words
 };
 
 // launchers (defined in the .cu files, called from api.cu)
+// Fused all-gather bookkeeping done by block 0 of the prep kernel (the first kernel of a call):
+// bump the slot's epoch and wait until every rank has acknowledged the previous one.
+struct GatherPrologue {
+  uint32_t* epoch;            // nullptr: not a fused-gather call
+  const uint32_t* ack_flags;  // this rank's ack flags [world]
+  int32_t world;
+  uint64_t timeout_ns;
+};
 cudaError_t launch_prep_queries(const float* q, int32_t n_queries, int64_t ldq, int32_t dim,
                                 int32_t normalize, int32_t round_bf16, float* out_f32,
                                 __nv_bfloat16* out_bf16, int32_t n_rows_padded, int32_t ld_out,
-                                int32_t* flags, cudaStream_t stream);
+                                int32_t* flags, const GatherPrologue& gp, cudaStream_t stream);
+const void* prep_kernel_handle();     // for CUDA-graph node patching (api.cu)
+constexpr int kPrepKernelParams = 12;
+const void* select_kernel_handle();
+cudaError_t launch_gather_wait(const uint32_t* my_flags, int32_t world, const uint32_t* epoch, int32_t* status,
+                               uint64_t timeout_ns, cudaStream_t stream);
+cudaError_t launch_sort_u64(uint64_t* keys, uint64_t* scratch, int64_t n, cudaStream_t stream);
+cudaError_t launch_row_norm_range(const float* x, int64_t n_rows, int32_t dim, int64_t ld, float* out_min_max,
+                                  int sm_count, cudaStream_t stream);
 cudaError_t launch_scan_gemv(const ScanParams& p, int32_t dtype, int mode, int sm_count,
                              cudaStream_t stream);
 cudaError_t launch_select(const SelectParams& p, int32_t n_queries, cudaStream_t stream);

@@ -223,11 +223,19 @@ cudaError_t launch_scan_gemv(const ScanParams& p, int32_t dtype, int mode, int s
 __global__ void __launch_bounds__(256) prep_queries_kernel(
     const float* __restrict__ q, int32_t n_queries, int64_t ldq, int32_t dim, int32_t normalize,
     int32_t round_bf16, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16,
-    int32_t n_rows_padded, int32_t ld_out, int32_t* flags) {
+    int32_t n_rows_padded, int32_t ld_out, int32_t* flags, const GatherPrologue gp) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   pdl_launch_dependents();
   pdl_wait();   // the previous search on this stream may still be reading the prepared queries
+  if (gp.epoch != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+    // fused all-gather: this call's sequence number on its slot (the same on every rank, calls are
+    // collective), and the guarantee that every rank has finished merging the previous use of the
+    // slot's gather buffers before this call's producer select overwrites them
+    const uint32_t epoch = *gp.epoch + 1u;
+    *gp.epoch = epoch;
+    wait_all_ge(gp.ack_flags, gp.world, epoch - 1u, flags, gp.timeout_ns);
+  }
   if (row >= n_rows_padded) return;
   float inv_den = 1.f;
   const bool real = row < n_queries;
@@ -264,12 +272,14 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(
 cudaError_t launch_prep_queries(const float* q, int32_t n_queries, int64_t ldq, int32_t dim,
                                 int32_t normalize, int32_t round_bf16, float* out_f32,
                                 __nv_bfloat16* out_bf16, int32_t n_rows_padded, int32_t ld_out,
-                                int32_t* flags, cudaStream_t stream) {
+                                int32_t* flags, const GatherPrologue& gp, cudaStream_t stream) {
   const int warps_per_block = 8;
   const int grid = (n_rows_padded + warps_per_block - 1) / warps_per_block;
   return launch_pdl(prep_queries_kernel, dim3(grid), dim3(warps_per_block * 32), 0, stream, q, n_queries,
-                    ldq, dim, normalize, round_bf16, out_f32, out_bf16, n_rows_padded, ld_out, flags);
+                    ldq, dim, normalize, round_bf16, out_f32, out_bf16, n_rows_padded, ld_out, flags, gp);
 }
+const void* prep_kernel_handle() { return reinterpret_cast<const void*>(prep_queries_kernel); }
+static_assert(kPrepKernelParams == 12, "api.cu patches parameter 0 of a kPrepKernelParams-parameter kernel");
 
 // ---- fp32 -> three bf16 planes (gallery ingest for the fp32 tensor-core path) ------------------------
 __global__ void __launch_bounds__(256) split_bf16x3_kernel(const float* __restrict__ src, int64_t n_rows, int32_t dim,

@@ -268,26 +268,23 @@ __device__ __forceinline__ void select_body(const SelectParams& p, SelShared& sh
 
 __device__ void select_dispatch(const SelectParams& p, SelShared& sh, uint64_t* list, int q);
 
-// ---- flags exchanged between GPUs (system scope) ----------------------------------------------------
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
+// The waits of the fused all-gather run in kernels of ONE warp, never inside the Q-CTA select
+// kernels: a select grid that spins occupies every SM once Q >= the SM count, and two searches in
+// flight on two streams could then wait for each other across ranks (rank A's slot-1 merge holds
+// A's SMs waiting for B's slot-1 keys while B's slot-2 merge holds B's SMs waiting for A's slot-2
+// keys, whose scan cannot get an SM).  A one-warp waiter leaves the machine to the scans.
+//   gather_wait_kernel  consumer side: every rank's keys of this epoch have landed here (ready >= epoch)
+//   (the producer side -- every rank has merged the previous use of this slot, ack >= epoch - 1 --
+//    is waited for by block 0 of prep_queries_kernel, the first kernel of the call)
+__global__ void __launch_bounds__(32) gather_wait_kernel(const uint32_t* my_flags, int32_t world,
+                                                         const uint32_t* epoch, int32_t* status, uint64_t timeout_ns) {
+  pdl_wait();   // NOT launch_dependents: the merge select must not be resident while this spins
+  if (threadIdx.x == 0) wait_all_ge(my_flags, world, *epoch, status, timeout_ns);
 }
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-// Wait until flags[i] >= want for every i in [0, n).  Bounded: a peer that never arrives must end
-// this kernel with a status flag, not hang the GPU (the waiters run on OTHER GPUs than the
-// producers they wait for, so this is not two kernels spinning on each other on one device).
-__device__ __forceinline__ void wait_all_ge(const uint32_t* flags, int n, uint32_t want, int32_t* status) {
-  for (int i = 0; i < n; ++i) {
-    uint32_t spins = 0;
-    while (static_cast<int32_t>(ld_acquire_sys(flags + i) - want) < 0) {
-      if (++spins > (1u << 22)) { atomicOr(status, kFlagWatchdog); return; }
-      __nanosleep(64);
-    }
-  }
+
+cudaError_t launch_gather_wait(const uint32_t* my_flags, int32_t world, const uint32_t* epoch, int32_t* status,
+                               uint64_t timeout_ns, cudaStream_t stream) {
+  return launch_pdl(gather_wait_kernel, dim3(1), dim3(32), 0, stream, my_flags, world, epoch, status, timeout_ns);
 }
 
 __global__ void __launch_bounds__(kSelThreads, 1) select_topk_kernel(const SelectParams p) {
@@ -298,18 +295,6 @@ __global__ void __launch_bounds__(kSelThreads, 1) select_topk_kernel(const Selec
   pdl_launch_dependents();
   pdl_wait();   // the list and its length come from the preceding scan
 
-  if (p.g_role != 0) {
-    // producer: every rank must have finished MERGING the previous use of this slot before its
-    //           buffer is overwritten (ack >= epoch - 1); consumer: every rank's keys of this epoch
-    //           must have landed here (ready >= epoch).
-    if (tid == 0) {
-      const uint32_t epoch = *p.g_epoch;
-      const uint32_t* mine = p.g_peer_flags[p.g_rank];
-      if (p.g_role == 1) wait_all_ge(mine + p.g_world, p.g_world, epoch - 1, p.flags);
-      else wait_all_ge(mine, p.g_world, epoch, p.flags);
-    }
-    __syncthreads();
-  }
   select_dispatch(p, sh, list, q);
   if (p.g_role != 0) {
     // last CTA out publishes: status word + "ready" (producer) or "ack" (consumer) to every rank
@@ -325,6 +310,14 @@ __global__ void __launch_bounds__(kSelThreads, 1) select_topk_kernel(const Selec
           for (int r = 0; r < p.g_world; ++r)
             p.g_peer_bufs[r][static_cast<int64_t>(p.g_rank) * p.g_list_stride + p.g_status_index] = status;
           __threadfence_system();
+        } else {
+          // the ranks' status words are copied out of the peer-writable buffer BEFORE the ack lets
+          // epoch + 1 producers overwrite it: the host reads this private snapshot
+          const uint64_t* mine = p.g_peer_bufs[p.g_rank];
+          for (int r = 0; r < p.g_world; ++r)
+            p.g_status_out[r] = static_cast<uint32_t>(
+                *reinterpret_cast<const volatile uint64_t*>(mine + static_cast<int64_t>(r) * p.g_list_stride + p.g_status_index));
+          __threadfence();
         }
         const int slot = (p.g_role == 1 ? 0 : p.g_world) + p.g_rank;
         for (int r = 0; r < p.g_world; ++r) st_release_sys(p.g_peer_flags[r] + slot, epoch);
@@ -363,6 +356,8 @@ __device__ __forceinline__ void select_dispatch_impl(const SelectParams& p, SelS
 __device__ void select_dispatch(const SelectParams& p, SelShared& sh, uint64_t* list, int q) {
   select_dispatch_impl(p, sh, list, q);
 }
+
+const void* select_kernel_handle() { return reinterpret_cast<const void*>(select_topk_kernel); }
 
 cudaError_t launch_select(const SelectParams& p, int32_t n_queries, cudaStream_t stream) {
   if (n_queries <= 0) return cudaSuccess;

@@ -97,7 +97,8 @@ class ShardedGallery:
     """
 
     def __init__(self, local, n_rows_global: int, group: Optional[dist.ProcessGroup] = None,
-                 local_search: Optional[Callable] = None, merge: Optional[Callable] = None):
+                 local_search: Optional[Callable] = None, merge: Optional[Callable] = None,
+                 fused: Optional[bool] = None):
         self.local = local
         self.n_rows_global = int(n_rows_global)
         self.group = group
@@ -106,11 +107,16 @@ class ShardedGallery:
         self._fast = local_search is None and merge is None   # product path: packed-key pipeline
         self._fused = {}
         import os
-        self._fused_ok = os.environ.get("MMRS_NO_FUSED_GATHER", "0") != "1"
+        self._fused_ok = os.environ.get("MMRS_NO_FUSED_GATHER", "0") != "1" if fused is None else bool(fused)
         if local_search is None:
             from .search import search_topk as local_search
         self._search = local_search
         self._merge = merge or _merge_cuda
+
+    @property
+    def fused_active(self) -> bool:
+        """True once a search of this handle has gone through the fused NVLink gather."""
+        return bool(self._fused) and self._fused_ok
 
     @classmethod
     def from_full(cls, features: torch.Tensor, mode: Optional[str] = None, device=None,
