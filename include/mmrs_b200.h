@@ -29,8 +29,14 @@
  *     caller-provided workspace whose size comes from the matching
  *     *_workspace_bytes() query.
  *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
- *     Calls are re-entrant; there is no global mutable state besides the
- *     thread-local error string and a per-thread pinned status word.
+ *     Calls may come from several threads.  Process-global state, all of it
+ *     internal and mutex-/atomic-protected: a cache of at most 32 instantiated
+ *     CUDA graphs keyed by the caller's workspace pointer (a search replays
+ *     the graph captured for its workspace; query / result pointers are
+ *     patched into it, they are not part of the key), the launch counter and
+ *     the profiling log of the measurement hooks.  Per thread: the error
+ *     string, one pinned status word, the device-attribute cache.  Two
+ *     searches in flight at the same time need two workspaces.
  *   - matrices are row-major; `ld_*` is the row stride in ELEMENTS.
  *   - there is no CPU fallback: on a device that is not compute capability 10.x
  *     every compute entry point returns MMRS_ERR_ARCH.
@@ -48,7 +54,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library itself is built with -fvisibility=hidden */
 #endif
 
-#define MMRS_ABI_VERSION 1
+#define MMRS_ABI_VERSION 2
 
 /* status codes */
 #define MMRS_OK 0
@@ -62,9 +68,11 @@ extern "C" {
 #define MMRS_ERR_CAPACITY (-6)   /* output capacity too small (self-join pair buffer);
                                     the required count is still reported             */
 #define MMRS_ERR_INTERNAL (-7)
-#define MMRS_ERR_RETRY (-8)      /* asynchronous search only: a candidate list overflowed and the
-                                    batch must be repeated through the synchronous entry point
-                                    (which then takes the exhaustive path)                     */
+#define MMRS_ERR_RETRY (-8)      /* a candidate list overflowed (scores correlated with the tile
+                                    stride pattern; rare): the results of this batch are invalid,
+                                    repeat it through mmrs_search_topk_exhaustive              */
+#define MMRS_ERR_TIMEOUT (-9)    /* fused all-gather: a peer rank did not arrive within
+                                    MMRS_GATHER_TIMEOUT_MS (default 20 000)                   */
 
 /* element types of the gallery / embedding matrix */
 #define MMRS_DTYPE_F32 0
@@ -119,6 +127,7 @@ size_t mmrs_search_workspace_bytes(int64_t n_rows, int32_t dim, int32_t gallery_
  * gallery_dtype BF16: the query is rounded to bf16 after normalisation (tensor-core mode);
  * F32: everything is fp32.
  * The call synchronises `stream` before returning (it must read back a status word).
+ * MMRS_ERR_RETRY: see mmrs_search_topk_exhaustive.
  */
 int mmrs_search_topk(const void* d_gallery, int64_t n_rows, int32_t dim, int64_t ld_gallery,
                      int32_t gallery_dtype, const float* d_queries, int32_t n_queries,
@@ -166,6 +175,20 @@ int mmrs_search_topk_host_async(const void* d_gallery, int64_t n_rows, int32_t d
 int mmrs_search_status(const int32_t* h_status);
 
 /*
+ * The exact fallback for a batch that returned MMRS_ERR_RETRY: one query at a time, every row's
+ * score becomes a key, one select over all of them (no thresholds, no candidate lists -- cannot
+ * overflow).  Needs its own, larger workspace (8 bytes per gallery row: 0.8 GB at 100M rows), which
+ * is why it is not part of every search workspace; allocate it for the call and free it again.
+ * Synchronises `stream`.
+ */
+size_t mmrs_search_exhaustive_workspace_bytes(int64_t n_rows, int32_t dim, int32_t n_queries);
+int mmrs_search_topk_exhaustive(const void* d_gallery, int64_t n_rows, int32_t dim, int64_t ld_gallery,
+                                int32_t gallery_dtype, const float* d_queries, int32_t n_queries,
+                                int64_t ld_queries, int32_t k, int32_t normalize_queries, float scale,
+                                int64_t index_offset, float* d_out_values, int64_t* d_out_indices,
+                                void* d_workspace, size_t workspace_bytes, void* stream);
+
+/*
  * Sharded search without a host round trip: each rank writes its local top-k as packed 64-bit keys
  * (order-preserving fp32 score in the high word, ~global_row in the low word; a larger key is a
  * better match and keys are unique), ONE all-gather moves n_queries * k * 8 bytes per rank, and
@@ -192,23 +215,29 @@ int mmrs_topk_merge_keys_async(const uint64_t* d_keys_in, int32_t n_lists, int32
  * every rank's LAST select stores its top-k_local keys directly into every rank's gather buffer
  * (d_peer_bufs[r] = rank r's buffer, peer-mapped, world * list_stride uint64; rank s owns the
  * slice [s * list_stride, +n_queries * k_local] plus one status word), the last CTA publishes a
- * "ready" flag to every rank with release semantics, and the merge select on each rank starts as
- * soon as all `world` flags carry this call's epoch -- no collective launch, no host round trip.
+ * "ready" flag to every rank with release semantics, a ONE-WARP kernel on each rank waits until all
+ * `world` flags carry this call's epoch, and the merge select then writes the global top-k_out --
+ * no collective launch, no host round trip, one CUDA graph per call.
  * d_peer_flags[r] = rank r's flag array (2 * world uint32, zero-initialised once): [0, world) ready,
- * [world, 2*world) ack (a rank acks after merging; producers wait for the acks of epoch - 1 before
- * overwriting a buffer).  `epoch` = 1, 2, 3, ... per (buffer, flag array) pair, identical on all
- * ranks; calls are collective: same order on every rank.  d_local_buf = this rank's own buffer.
- * h_status: pinned int32 [2 * world + 2]; after the stream has completed,
+ * [world, 2*world) ack (a rank acks after merging and after it has copied the ranks' status words to
+ * private memory; the first kernel of the next call on the slot waits for the acks of the previous
+ * epoch before any buffer is overwritten).  d_local_buf / d_local_flags = this rank's own buffer and
+ * flag array (local addresses).  The epoch is a counter in the WORKSPACE, bumped on the device by every
+ * call: the workspace must be zero-filled once before its first use and belongs to one (shape, stream)
+ * slot; calls on a slot are collective -- same order on every rank.  No spinning CTA ever occupies
+ * more than one warp, so searches in flight on several streams cannot starve each other.
+ * h_status: pinned int32 [world + 2]; after the stream has completed,
  * mmrs_gather_status(h_status, world) is the outcome on every rank alike (MMRS_ERR_RETRY when any
- * rank overflowed).  n_queries <= 1024.
+ * rank overflowed; MMRS_ERR_TIMEOUT when a peer never arrived).  n_queries <= 1024, world <= 64,
+ * k_local must be the same on every rank.
  */
 int mmrs_search_topk_fused_gather_async(
     const void* d_gallery, int64_t n_rows, int32_t dim, int64_t ld_gallery, int32_t gallery_dtype,
     const float* d_queries, int32_t n_queries, int64_t ld_queries, int32_t k_local, int32_t k_out,
     int32_t normalize_queries, float scale, int64_t index_offset, int32_t path,
-    uint64_t* const* d_peer_bufs, uint32_t* const* d_peer_flags, uint64_t* d_local_buf, int32_t rank,
-    int32_t world, int64_t list_stride, uint32_t epoch, float* d_out_values, int64_t* d_out_indices,
-    void* d_workspace, size_t workspace_bytes, int32_t* h_status, void* stream);
+    uint64_t* const* d_peer_bufs, uint32_t* const* d_peer_flags, uint64_t* d_local_buf,
+    uint32_t* d_local_flags, int32_t rank, int32_t world, int64_t list_stride, float* d_out_values,
+    int64_t* d_out_indices, void* d_workspace, size_t workspace_bytes, int32_t* h_status, void* stream);
 int mmrs_gather_status(const int32_t* h_status, int32_t world);
 
 /* ---- multi-GPU merge -------------------------------------------------------------------- */
@@ -227,7 +256,7 @@ int mmrs_topk_merge(const float* d_values_in, const int64_t* d_indices_in, int32
 
 /* ---- near-duplicate self-join ---------------------------------------------------------- */
 
-size_t mmrs_selfjoin_workspace_bytes(int64_t n_rows, int32_t dim, int32_t dtype);
+size_t mmrs_selfjoin_workspace_bytes(int64_t n_rows, int32_t dim, int32_t dtype); /* 0: none needed */
 
 /*
  * All pairs (i, j), i < j, row_begin <= i < row_end, with <e_i, e_j> >= threshold, where the
@@ -261,6 +290,23 @@ int mmrs_selfjoin_pairs_tc(const float* d_emb_f32, int64_t ld_f32, const void* d
                            int64_t capacity, int64_t* d_out_count, int64_t cand_capacity,
                            void* d_workspace, size_t workspace_bytes, void* stream);
 
+/*
+ * Lexicographic (i, j) sort of an int64 [n_pairs, 2] pair list in place -- the order of
+ * `triu(S >= tau, 1).nonzero()`.  Row ids must fit 32 bits.  Workspace:
+ * mmrs_sort_pairs_workspace_bytes(n_pairs).  Asynchronous on `stream`.
+ */
+size_t mmrs_sort_pairs_workspace_bytes(int64_t n_pairs);
+int mmrs_sort_pairs(int64_t* d_pairs, int64_t n_pairs, void* d_workspace, size_t workspace_bytes,
+                    void* stream);
+
+/*
+ * d_out_min_max[0 / 1] = smallest / largest L2 norm over the rows of d_emb (fp32).  The tensor-core
+ * join's margin bounds the bf16 rounding of UNIT rows; callers scale it by max_norm^2 (or refuse)
+ * when rows are not unit-norm.  Asynchronous on `stream`.
+ */
+int mmrs_row_norm_range(const float* d_emb, int64_t n_rows, int32_t dim, int64_t ld,
+                        float* d_out_min_max, void* stream);
+
 /* ---- threshold / F1 sweep (the reference's consumer of the scores) ------------------ */
 
 /*
@@ -277,6 +323,12 @@ int mmrs_threshold_sweep(const float* d_pos, int64_t n_pos, const float* d_neg, 
                          const double* d_thresholds, int32_t n_thresholds,
                          int64_t* d_out_counts, void* d_workspace, size_t workspace_bytes,
                          void* stream);
+
+/* float64 scores (a numpy float64 array compared with the fp64 grid: no rounding on the way in). */
+int mmrs_threshold_sweep_f64(const double* d_pos, int64_t n_pos, const double* d_neg, int64_t n_neg,
+                             const double* d_thresholds, int32_t n_thresholds,
+                             int64_t* d_out_counts, void* d_workspace, size_t workspace_bytes,
+                             void* stream);
 
 /*
  * The same sweep without any N-sized host traffic: d_scores [n] fp32 and d_targets [n] int64 stay on
@@ -297,6 +349,10 @@ int mmrs_threshold_sweep_labeled(const float* d_scores, const int64_t* d_targets
 
 /* Number of kernels this library has launched in this process (monotonic). */
 int64_t mmrs_launch_count(void);
+
+/* h_out4 = { graph captures, graph replays, replays that re-pointed query/result nodes, captures whose
+ * nodes could not be identified for patching } since process start. */
+int mmrs_graph_stats(int64_t* h_out4);
 
 /*
  * While enabled, every gallery-scan kernel launch (K1 / K2; the HBM- or tensor-bound kernels) is

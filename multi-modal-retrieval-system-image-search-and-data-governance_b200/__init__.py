@@ -4,7 +4,11 @@ chy980959830/Multi-Modal-Retrieval-System-Image-Search-and-Data-Governance.
 Import as `mmrs_b200` (see ../mmrs_b200.py).  The public names mirror the reference's module-level
 functions for this path (same names, positional order and return tuples):
 
-    code/search_image.py   get_similarity, construct_dataset, eval_threshold, find_thresholds
+    code/search_image.py   get_similarity, construct_dataset, eval_threshold, find_thresholds,
+                           get_image_text_features, get_cluster_features (+ their arithmetic on encoded
+                           features: image_text_prototypes, cluster_prototype, outlier_filter_features)
+    code/utils.py          cls_acc (top-k of an existing score matrix: topk_of_scores)
+    code/merge_dataset.py  cosine_similarity_scores (logit_scale * F.cosine_similarity, :275-278)
     tool/find_repeated.py  get_all_images, find_and_remove_duplicate_images
     tool/find_repeated_in_same_folder.py
                            find_and_remove_duplicate_images (same-folder form)
@@ -21,15 +25,19 @@ DeviceGallery, ShardedGallery.  Everything computes through the C-ABI CUDA libra
 """
 from . import _cabi  # noqa: F401  (fails loudly when the CUDA library is missing)
 from .gallery import DeviceGallery, load_feature_cache
-from .search import (best_threshold_on_device, calc_combined_metrics, construct_dataset, eval_threshold, evaluate_thresholds, find_thresholds, full_scores,
-                     get_similarity, get_similarity_from_matrix, mix_image_text_query, outlier_filter_features, score_classes, search_topk,
-                     threshold_sweep_counts)
-from .dedup import (detect_and_remove_cross_set_duplicates, find_and_remove_duplicate_images, find_duplicate_pairs,
-                    find_and_remove_near_duplicate_images, get_all_images, greedy_first_keeper)
+from .search import (best_threshold_on_device, calc_combined_metrics, cls_acc, cluster_prototype, construct_dataset,
+                     cosine_similarity_scores, eval_threshold, evaluate_thresholds, find_thresholds, full_scores,
+                     get_cluster_features, get_image_text_features, get_similarity, get_similarity_from_matrix,
+                     image_text_prototypes, mix_image_text_query, outlier_filter_features, score_classes, search_topk,
+                     threshold_sweep_counts, topk_of_scores)
+from .dedup import (calculate_image_hash, detect_and_remove_cross_set_duplicates, find_and_remove_duplicate_images,
+                    find_duplicate_pairs, find_and_remove_near_duplicate_images, get_all_images, greedy_first_keeper)
 from .sharded import ShardedGallery, shard_bounds
 
 __all__ = [
-    "DeviceGallery", "ShardedGallery", "best_threshold_on_device", "calc_combined_metrics", "construct_dataset",
+    "DeviceGallery", "ShardedGallery", "best_threshold_on_device", "calc_combined_metrics", "calculate_image_hash", "cls_acc",
+    "cluster_prototype", "construct_dataset", "cosine_similarity_scores", "get_cluster_features", "get_image_text_features",
+    "image_text_prototypes", "topk_of_scores",
     "detect_and_remove_cross_set_duplicates", "evaluate_thresholds", "eval_threshold", "find_thresholds",
     "find_and_remove_duplicate_images", "find_and_remove_near_duplicate_images",
     "find_duplicate_pairs", "full_scores", "get_all_images", "get_similarity", "get_similarity_from_matrix",

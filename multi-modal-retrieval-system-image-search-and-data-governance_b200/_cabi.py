@@ -9,7 +9,8 @@ _PKG_DIR = Path(__file__).resolve().parent
 LIB_PATH = _PKG_DIR / "lib" / "libmmrs_b200.so"
 
 OK = 0
-ERR_ARG, ERR_CUDA, ERR_ARCH, ERR_WORKSPACE, ERR_ZERO_NORM, ERR_CAPACITY, ERR_INTERNAL, ERR_RETRY = -1, -2, -3, -4, -5, -6, -7, -8
+ERR_ARG, ERR_CUDA, ERR_ARCH, ERR_WORKSPACE, ERR_ZERO_NORM, ERR_CAPACITY, ERR_INTERNAL, ERR_RETRY, ERR_TIMEOUT = -1, -2, -3, -4, -5, -6, -7, -8, -9
+ABI_VERSION = 2
 DTYPE_F32, DTYPE_BF16, DTYPE_BF16X3 = 0, 1, 2
 PATH_AUTO, PATH_GEMV, PATH_MMA = 0, 1, 2
 PATHS = {"auto": PATH_AUTO, "gemv": PATH_GEMV, "mma": PATH_MMA}
@@ -57,8 +58,11 @@ SIGNATURES = {
     "mmrs_search_topk_host_async": (C.c_int, [_vp, _i64, _i32, _i64, _i32, _vp, _i32, _i64, _i32, _i32,
                                               _f32, _i64, _i32, _vp, _vp, _vp, _sz, _vp, _vp]),
     "mmrs_search_status": (C.c_int, [_vp]),
+    "mmrs_search_exhaustive_workspace_bytes": (_sz, [_i64, _i32, _i32]),
+    "mmrs_search_topk_exhaustive": (C.c_int, [_vp, _i64, _i32, _i64, _i32, _vp, _i32, _i64, _i32, _i32, _f32,
+                                              _i64, _vp, _vp, _vp, _sz, _vp]),
     "mmrs_search_topk_fused_gather_async": (C.c_int, [_vp, _i64, _i32, _i64, _i32, _vp, _i32, _i64, _i32, _i32, _i32,
-                                                      _f32, _i64, _i32, _vp, _vp, _vp, _i32, _i32, _i64, C.c_uint32,
+                                                      _f32, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _i64,
                                                       _vp, _vp, _vp, _sz, _vp, _vp]),
     "mmrs_gather_status": (C.c_int, [_vp, _i32]),
     "mmrs_search_topk_keys_async": (C.c_int, [_vp, _i64, _i32, _i64, _i32, _vp, _i32, _i64, _i32, _i32, _f32,
@@ -72,6 +76,11 @@ SIGNATURES = {
     "mmrs_selfjoin_tc_workspace_bytes": (_sz, [_i64, _i64]),
     "mmrs_selfjoin_pairs_tc": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i32, _f32, _f32, _i32, _i32, _vp, _i64,
                                          _vp, _i64, _vp, _sz, _vp]),
+    "mmrs_sort_pairs_workspace_bytes": (_sz, [_i64]),
+    "mmrs_sort_pairs": (C.c_int, [_vp, _i64, _vp, _sz, _vp]),
+    "mmrs_row_norm_range": (C.c_int, [_vp, _i64, _i32, _i64, _vp, _vp]),
+    "mmrs_graph_stats": (C.c_int, [_vp]),
+    "mmrs_threshold_sweep_f64": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i32, _vp, _vp, _sz, _vp]),
     "mmrs_threshold_sweep_workspace_bytes": (_sz, [_i32]),
     "mmrs_launch_count": (_i64, []),
     "mmrs_profile_enable": (C.c_int, [C.c_int]),

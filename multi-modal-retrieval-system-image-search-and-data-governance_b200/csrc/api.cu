@@ -24,6 +24,10 @@ cudaError_t launch_selfjoin_f32(const float* emb, int64_t n_rows, int32_t dim, i
 cudaError_t launch_threshold_sweep(const float* pos, int64_t n_pos, const float* neg, int64_t n_neg,
                                    const double* thr, int32_t n_thr, int64_t* out_counts,
                                    unsigned long long* hist_ws, int sm_count, cudaStream_t stream);
+cudaError_t launch_threshold_sweep_f64(const double* pos, int64_t n_pos, const double* neg, int64_t n_neg,
+                                       const double* thr, int32_t n_thr, int64_t* out_counts,
+                                       unsigned long long* hist_ws, int sm_count, cudaStream_t stream);
+cudaError_t launch_sort_pairs(int64_t* pairs, int64_t n_pairs, uint64_t* scratch, cudaStream_t stream);
 cudaError_t launch_threshold_sweep_labeled(const float* scores, const int64_t* targets, int64_t label, int64_t n,
                                            int32_t n_thr, int32_t grid_f32, double* thr_out, int64_t* out_counts,
                                            unsigned long long* hist_ws, uint32_t* mm_ws, int sm_count,
@@ -104,7 +108,7 @@ struct DeviceInfo {
 };
 
 static int current_device(DeviceInfo* info) {
-  static DeviceInfo cache[64];
+  static thread_local DeviceInfo cache[64];
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess)
@@ -163,19 +167,25 @@ struct Workspace {
   uint32_t* cnt;           // [Qs]
   uint64_t* cand;          // [Qs, cap] (>= n_tiles * kTileRows keys for the exhaustive path)
   size_t cand_keys;
-  uint32_t* gscratch;      // [8]: [0] epoch, [1] producer CTA counter, [2] consumer CTA counter, [4] merge status
+  uint32_t* gscratch;      // [kGScratch] fused all-gather bookkeeping, see below
   size_t total;
 };
+// gscratch words: [0] epoch of the slot (bumped by the prep kernel of every fused call; the caller
+// zero-fills a workspace once, before its first use) [1] producer CTA counter [2] consumer CTA counter
+// [8, 8 + world) snapshot of the ranks' status words [8 + world] status of the merge select
+constexpr int kGScratch = 128;
+constexpr int kGStatus = 8;
+constexpr int kMaxWorld = 64;
 
 static Workspace carve(void* base, int64_t n_rows, int32_t dim, int32_t n_queries, int32_t k,
-                       bool with_lists) {
+                       bool with_lists, bool exhaustive = false) {
   Workspace w{};
   size_t off = 0;
   char* b = static_cast<char*>(base);
   auto take = [&](size_t bytes) { char* p = b ? b + off : nullptr; off += align_up(bytes, 256); return p; };
   const int32_t ldq = padded_dim(dim), qp = padded_queries(n_queries);
   w.flags = reinterpret_cast<int32_t*>(take(8 * sizeof(int32_t)));
-  w.gscratch = reinterpret_cast<uint32_t*>(take(8 * sizeof(uint32_t)));
+  w.gscratch = reinterpret_cast<uint32_t*>(take(kGScratch * sizeof(uint32_t)));
   w.q_f32 = reinterpret_cast<float*>(take(static_cast<size_t>(qp) * ldq * sizeof(float)));
   w.q_bf16 = reinterpret_cast<__nv_bfloat16*>(take(3 * static_cast<size_t>(qp) * ldq * sizeof(__nv_bfloat16)));   // up to 3 planes
   if (with_lists) {
@@ -183,9 +193,9 @@ static Workspace carve(void* base, int64_t n_rows, int32_t dim, int32_t n_querie
     const int32_t qs = n_queries < kSuperChunk ? n_queries : kSuperChunk;
     w.thr = reinterpret_cast<float*>(take(static_cast<size_t>(qs) * sizeof(float)));
     w.cnt = reinterpret_cast<uint32_t*>(take(static_cast<size_t>(qs) * sizeof(uint32_t)));
-    size_t keys = static_cast<size_t>(qs) * pl.cap;
-    const size_t exhaustive = static_cast<size_t>(pl.n_tiles) * kTileRows;
-    if (keys < exhaustive) keys = exhaustive;
+    // the exhaustive re-run (one query at a time, every row a key) needs n_tiles * 128 keys -- 0.8 GB
+    // at 100M rows -- and is carved only for mmrs_search_topk_exhaustive's own, temporary workspace
+    size_t keys = exhaustive ? static_cast<size_t>(pl.n_tiles) * kTileRows : static_cast<size_t>(qs) * pl.cap;
     w.cand_keys = keys;
     w.cand = reinterpret_cast<uint64_t*>(take(keys * sizeof(uint64_t)));
   }
@@ -312,12 +322,37 @@ struct SearchArgs {
   int32_t k; int32_t normalize; float scale; int64_t index_offset; int32_t path;
   float* d_values; int64_t* d_indices;
   uint64_t* d_keys = nullptr;   // optional: packed (score, ~global row) keys instead of / besides the pair
-  // fused all-gather (producer side of the last select)
+  // fused all-gather: the last local select stores into every rank's gather buffer (producer), a
+  // one-warp kernel waits for every rank's keys, a merge select over this rank's buffer (consumer)
+  // writes d_values / d_indices [n_queries, g_k_out]
   int32_t g_world = 0, g_rank = 0;
   uint64_t* const* g_peer_bufs = nullptr;
   uint32_t* const* g_peer_flags = nullptr;
+  uint64_t* g_local_buf = nullptr;
+  uint32_t* g_local_flags = nullptr;
   int64_t g_list_stride = 0;
+  int32_t g_k_out = 0;
+  uint64_t g_timeout_ns = 0;
 };
+
+static uint64_t gather_timeout_ns() {
+  const int ms = env_int("MMRS_GATHER_TIMEOUT_MS", 20000);
+  return static_cast<uint64_t>(ms < 1 ? 1 : ms) * 1000000ull;
+}
+
+static int enqueue_prep(const SearchArgs& a, const Workspace& w, cudaStream_t stream) {
+  const int32_t ldq = padded_dim(a.dim), qp = padded_queries(a.n_queries);
+  GatherPrologue gp{};
+  if (a.g_world > 0) {
+    gp.epoch = w.gscratch; gp.ack_flags = a.g_local_flags + a.g_world; gp.world = a.g_world;
+    gp.timeout_ns = a.g_timeout_ns;
+  }
+  return profiled_launch(4, 0, 0, stream, [&]() {
+    return launch_prep_queries(a.d_queries, a.n_queries, a.ldq_in, a.dim, a.normalize,
+                               a.dtype == MMRS_DTYPE_BF16 ? 1 : (a.dtype == MMRS_DTYPE_BF16X3 ? 2 : 0), w.q_f32, w.q_bf16, qp, ldq,
+                               w.flags, gp, stream);
+  });
+}
 
 // Enqueue the whole fused search on `stream`.  Results are valid iff the flag word stays 0.
 static int enqueue_search(const SearchArgs& a, const DeviceInfo& dev, const Workspace& w,
@@ -327,14 +362,13 @@ static int enqueue_search(const SearchArgs& a, const DeviceInfo& dev, const Work
   const Path path = choose_path(a.path, a.dtype, a.n_queries);
   if (path == Path::kMma && a.dtype == MMRS_DTYPE_F32)
     return fail(MMRS_ERR_ARG, "MMRS_PATH_MMA needs a bf16 (or bf16x3) gallery");
+  const bool fused = a.g_world > 0;
 
   MMRS_CUDA(cudaMemsetAsync(w.flags, 0, 8 * sizeof(int32_t), stream));
+  if (fused)   // status snapshot + merge status of this call (the epoch and the CTA counters persist)
+    MMRS_CUDA(cudaMemsetAsync(w.gscratch + kGStatus, 0, (kMaxWorld + 1) * sizeof(uint32_t), stream));
   {
-    int rc = profiled_launch(4, 0, 0, stream, [&]() {
-      return launch_prep_queries(a.d_queries, a.n_queries, a.ldq_in, a.dim, a.normalize,
-                                 a.dtype == MMRS_DTYPE_BF16 ? 1 : (a.dtype == MMRS_DTYPE_BF16X3 ? 2 : 0), w.q_f32, w.q_bf16, qp, ldq,
-                                 w.flags, stream);
-    });
+    int rc = enqueue_prep(a, w, stream);
     if (rc != MMRS_OK) return rc;
   }
   ScanParams base{};
@@ -360,12 +394,14 @@ static int enqueue_search(const SearchArgs& a, const DeviceInfo& dev, const Work
       sp.fixed_n = ph == 0 ? pl.dense_rows : -1;
       sp.k = a.k;
       sp.final_pass = ph == pl.n_phases - 1;
-      sp.out_values = a.d_values ? a.d_values + static_cast<int64_t>(s0) * a.k : nullptr;
-      sp.out_indices = a.d_indices ? a.d_indices + static_cast<int64_t>(s0) * a.k : nullptr;
-      sp.out_keys = a.d_keys ? a.d_keys + static_cast<int64_t>(s0) * a.k : nullptr;
+      if (!fused) {
+        sp.out_values = a.d_values ? a.d_values + static_cast<int64_t>(s0) * a.k : nullptr;
+        sp.out_indices = a.d_indices ? a.d_indices + static_cast<int64_t>(s0) * a.k : nullptr;
+        sp.out_keys = a.d_keys ? a.d_keys + static_cast<int64_t>(s0) * a.k : nullptr;
+      }
       sp.index_offset = a.index_offset;
       sp.flags = w.flags;
-      if (a.g_world > 0 && sp.final_pass) {
+      if (fused && sp.final_pass) {
         sp.g_role = 1; sp.g_world = a.g_world; sp.g_rank = a.g_rank;
         sp.g_peer_bufs = a.g_peer_bufs; sp.g_peer_flags = a.g_peer_flags;
         sp.g_list_stride = a.g_list_stride; sp.g_status_index = a.n_queries * a.k;
@@ -375,11 +411,30 @@ static int enqueue_search(const SearchArgs& a, const DeviceInfo& dev, const Work
       if (rc != MMRS_OK) return rc;
     }
   }
+  if (fused) {
+    int32_t* merge_status = reinterpret_cast<int32_t*>(w.gscratch + kGStatus + a.g_world);
+    int rc = profiled_launch(5, 0, 0, stream, [&]() {
+      return launch_gather_wait(a.g_local_flags, a.g_world, w.gscratch, merge_status, a.g_timeout_ns, stream);
+    });
+    if (rc != MMRS_OK) return rc;
+    // consumer: merge the lists every rank stored into MY gather buffer
+    SelectParams sp{};
+    sp.cand = a.g_local_buf;
+    sp.cap = a.g_world * a.k; sp.fixed_n = a.g_world * a.k; sp.k = a.g_k_out; sp.final_pass = 1;
+    sp.out_values = a.d_values; sp.out_indices = a.d_indices; sp.index_offset = 0;
+    sp.flags = merge_status;
+    sp.seg_len = a.k; sp.seg_stride = a.g_list_stride;
+    sp.g_role = 2; sp.g_world = a.g_world; sp.g_rank = a.g_rank; sp.g_peer_bufs = a.g_peer_bufs; sp.g_peer_flags = a.g_peer_flags;
+    sp.g_list_stride = a.g_list_stride; sp.g_status_index = a.n_queries * a.k;
+    sp.g_epoch = w.gscratch; sp.g_counter = w.gscratch + 2; sp.g_status_out = w.gscratch + kGStatus;
+    rc = profiled_launch(3, 0, 0, stream, [&]() { return launch_select(sp, a.n_queries, stream); });
+    if (rc != MMRS_OK) return rc;
+  }
   return MMRS_OK;
 }
 
 // Slow exact path for when a candidate list overflowed: one query at a time, every score
-// becomes a key, one select over all of them.
+// becomes a key, one select over all of them.  `w` is carved with exhaustive = true.
 static int enqueue_exhaustive(const SearchArgs& a, const DeviceInfo& dev, const Workspace& w,
                               cudaStream_t stream) {
   const SearchPlan pl = plan_for(a.n_rows, a.k, a.n_queries);
@@ -391,6 +446,10 @@ static int enqueue_exhaustive(const SearchArgs& a, const DeviceInfo& dev, const 
   base.cap = all_rows;
   base.sched = TileSchedule{pl.n_tiles, 1, 0, pl.n_tiles};
   MMRS_CUDA(cudaMemsetAsync(w.flags, 0, 8 * sizeof(int32_t), stream));
+  {
+    int rc = enqueue_prep(a, w, stream);
+    if (rc != MMRS_OK) return rc;
+  }
   for (int32_t q = 0; q < a.n_queries; ++q) {
     ScanParams p = base;
     p.cand = w.cand - static_cast<int64_t>(q) * all_rows;
@@ -415,22 +474,30 @@ static int enqueue_exhaustive(const SearchArgs& a, const DeviceInfo& dev, const 
 // A search is 7-9 short dependent launches in front of one long one; submitted one by one the GPU
 // idles between them (the host needs ~60 us to issue what the GPU runs in ~40 us, measured:
 // profiles/r01_v1_bench.json whole step 0.31 ms vs 0.24 ms of kernels).  The whole sequence
-// is therefore captured once per distinct call signature and replayed with one cudaGraphLaunch.
-// Everything baked into the graph -- pointers, shapes, scalars -- is part of the key.
+// is therefore captured once per workspace slot and call signature and replayed with one
+// cudaGraphLaunch.  The key is the WORKSPACE (one per search shape and stream) plus everything that
+// shapes the launches; the caller's query and result pointers are NOT part of it: they appear in
+// exactly two kinds of kernel node -- the prep kernel reads d_queries, the final select(s) write
+// d_values / d_indices / d_keys -- and those nodes are re-pointed with
+// cudaGraphExecKernelNodeSetParams when a call brings other tensors.  A caller that keeps every result
+// tensor therefore still replays one graph (tests/test_search_gpu.py::test_retained_outputs_capture_once).
 struct GraphKey {
   const void* gallery; int64_t n_rows; int32_t dim; int64_t ld; int32_t dtype;
-  const float* d_queries; int32_t n_queries; int64_t ldq_in; int32_t k; int32_t normalize;
-  float scale; int64_t index_offset; int32_t path; float* d_values; int64_t* d_indices;
-  void* workspace; int device; int ratio_log2; int dense_tiles; uint64_t* d_keys;
-  int32_t g_world, g_rank; const void* g_bufs; const void* g_flags; int64_t g_stride;
+  int32_t n_queries; int64_t ldq_in; int32_t k; int32_t normalize;
+  float scale; int64_t index_offset; int32_t path;
+  void* workspace; int device; int ratio_log2; int dense_tiles;
+  bool has_values, has_indices, has_keys;
+  int32_t g_world, g_rank; const void* g_bufs; const void* g_flags; const void* g_local_buf; const void* g_local_flags;
+  int64_t g_stride; int32_t g_k_out; uint64_t g_timeout_ns;
   uint64_t knobs;   // the kernel-shape environment knobs the captured launches were configured with
   bool operator==(const GraphKey& o) const {
     return knobs == o.knobs && g_world == o.g_world && g_rank == o.g_rank && g_bufs == o.g_bufs && g_flags == o.g_flags &&
-           g_stride == o.g_stride && d_keys == o.d_keys && gallery == o.gallery && n_rows == o.n_rows && dim == o.dim && ld == o.ld && dtype == o.dtype &&
-           d_queries == o.d_queries && n_queries == o.n_queries && ldq_in == o.ldq_in && k == o.k &&
+           g_local_buf == o.g_local_buf && g_local_flags == o.g_local_flags && g_stride == o.g_stride && g_k_out == o.g_k_out &&
+           g_timeout_ns == o.g_timeout_ns && has_values == o.has_values && has_indices == o.has_indices &&
+           has_keys == o.has_keys && gallery == o.gallery && n_rows == o.n_rows && dim == o.dim && ld == o.ld &&
+           dtype == o.dtype && n_queries == o.n_queries && ldq_in == o.ldq_in && k == o.k &&
            normalize == o.normalize && scale == o.scale && index_offset == o.index_offset &&
-           path == o.path && d_values == o.d_values && d_indices == o.d_indices &&
-           workspace == o.workspace && device == o.device && ratio_log2 == o.ratio_log2 &&
+           path == o.path && workspace == o.workspace && device == o.device && ratio_log2 == o.ratio_log2 &&
            dense_tiles == o.dense_tiles;
   }
 };
@@ -438,7 +505,8 @@ struct GraphKey {
 // side): a graph captured under one setting must not be replayed under another
 static uint64_t knob_hash() {
   static const char* const kNames[] = {"MMRS_K2_SMALL_MAX", "MMRS_K2_BIG_SMEM", "MMRS_K2_CTAS_PER_SM", "MMRS_K2_QCHUNKS",
-                                       "MMRS_K2_NO_PAIR", "MMRS_K2_PAIR_MIN", "MMRS_K2_DEBUG_SKIP_EPI", "MMRS_NO_PDL"};
+                                       "MMRS_K2_NO_PAIR", "MMRS_K2_PAIR_MIN", "MMRS_K2_DEBUG_SKIP_EPI", "MMRS_NO_PDL",
+                                       "MMRS_K2_QRES", "MMRS_K2_STAGES"};
   uint64_t h = 1469598103934665603ull;
   for (const char* name : kNames) {
     const char* v = getenv(name);
@@ -447,57 +515,145 @@ static uint64_t knob_hash() {
   }
   return h;
 }
-struct GraphEntry { GraphKey key; cudaGraphExec_t exec; uint64_t stamp; long long kernels; };
+enum SiteKind { kSitePrep = 0, kSiteFinalSelect = 1 };
+struct PatchSite { cudaGraphNode_t node; int kind; int64_t s0; };
+struct GraphEntry {
+  GraphKey key; cudaGraph_t graph; cudaGraphExec_t exec; uint64_t stamp; long long kernels;
+  std::vector<PatchSite> sites; bool patchable;
+  const float* q; float* v; int64_t* i; uint64_t* keys;   // the pointers the executable graph currently holds
+};
 static std::mutex g_graph_mu;
 static std::vector<GraphEntry> g_graphs;
 static uint64_t g_graph_clock = 0;
 constexpr size_t kMaxGraphs = 32;
+static std::atomic<long long> g_stat_captures{0}, g_stat_replays{0}, g_stat_patches{0}, g_stat_unpatchable{0};
+
+// Find the kernel nodes that hold caller pointers.  False when the graph does not look as expected
+// (then the entry only serves calls with exactly the captured pointers).
+static bool discover_sites(cudaGraph_t graph, const SearchArgs& a, std::vector<PatchSite>* sites) {
+  size_t n = 0;
+  if (cudaGraphGetNodes(graph, nullptr, &n) != cudaSuccess || n == 0) { cudaGetLastError(); return false; }
+  std::vector<cudaGraphNode_t> nodes(n);
+  if (cudaGraphGetNodes(graph, nodes.data(), &n) != cudaSuccess) { cudaGetLastError(); return false; }
+  const int32_t k_out = a.g_world > 0 ? a.g_k_out : a.k;
+  int n_prep = 0, n_final = 0;
+  for (cudaGraphNode_t node : nodes) {
+    cudaGraphNodeType t;
+    if (cudaGraphNodeGetType(node, &t) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (t != cudaGraphNodeTypeKernel) continue;
+    cudaKernelNodeParams kp{};
+    if (cudaGraphKernelNodeGetParams(node, &kp) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (kp.func == prep_kernel_handle()) {
+      if (!kp.kernelParams || *static_cast<const float* const*>(kp.kernelParams[0]) != a.d_queries) return false;
+      sites->push_back(PatchSite{node, kSitePrep, 0});
+      ++n_prep;
+    } else if (kp.func == select_kernel_handle()) {
+      if (!kp.kernelParams) return false;
+      const SelectParams* sp = static_cast<const SelectParams*>(kp.kernelParams[0]);
+      if (!sp->final_pass || (a.g_world > 0 && sp->g_role != 2)) continue;
+      int64_t off = -1;
+      if (a.d_values && sp->out_values) off = sp->out_values - a.d_values;
+      else if (a.d_indices && sp->out_indices) off = sp->out_indices - a.d_indices;
+      else if (a.d_keys && sp->out_keys) off = static_cast<int64_t>(sp->out_keys - a.d_keys);
+      if (off < 0 || off % k_out != 0) return false;
+      sites->push_back(PatchSite{node, kSiteFinalSelect, off / k_out});
+      ++n_final;
+    }
+  }
+  const int want_final = a.g_world > 0 ? 1 : (a.n_queries + kSuperChunk - 1) / kSuperChunk;
+  return n_prep == 1 && n_final == want_final;
+}
+
+static int patch_entry(GraphEntry& e, const SearchArgs& a) {
+  const int32_t k_out = a.g_world > 0 ? a.g_k_out : a.k;
+  for (const PatchSite& site : e.sites) {
+    cudaKernelNodeParams kp{};
+    MMRS_CUDA(cudaGraphKernelNodeGetParams(site.node, &kp));
+    void* params[kPrepKernelParams];
+    if (site.kind == kSitePrep) {
+      for (int i = 0; i < kPrepKernelParams; ++i) params[i] = kp.kernelParams[i];
+      const float* q = a.d_queries;
+      params[0] = &q;
+      kp.kernelParams = params;
+      MMRS_CUDA(cudaGraphExecKernelNodeSetParams(e.exec, site.node, &kp));
+    } else {
+      SelectParams sp = *static_cast<const SelectParams*>(kp.kernelParams[0]);
+      sp.out_values = a.d_values ? a.d_values + site.s0 * k_out : nullptr;
+      sp.out_indices = a.d_indices ? a.d_indices + site.s0 * k_out : nullptr;
+      if (a.g_world == 0) sp.out_keys = a.d_keys ? a.d_keys + site.s0 * k_out : nullptr;
+      params[0] = &sp;
+      kp.kernelParams = params;
+      MMRS_CUDA(cudaGraphExecKernelNodeSetParams(e.exec, site.node, &kp));
+    }
+  }
+  e.q = a.d_queries; e.v = a.d_values; e.i = a.d_indices; e.keys = a.d_keys;
+  g_stat_patches.fetch_add(1);
+  return MMRS_OK;
+}
 
 static int launch_search_graph(const SearchArgs& a, const DeviceInfo& dev, const Workspace& w,
                                void* workspace, cudaStream_t stream) {
   if (g_prof_on.load(std::memory_order_relaxed) || env_int("MMRS_NO_GRAPH", 0))
     return enqueue_search(a, dev, w, stream);   // event-bracketed launches are issued directly
-  GraphKey key{a.gallery, a.n_rows, a.dim, a.ld, a.dtype, a.d_queries, a.n_queries, a.ldq_in, a.k,
-               a.normalize, a.scale, a.index_offset, a.path, a.d_values, a.d_indices, workspace,
-               dev.device, env_int("MMRS_RATIO_LOG2", -1), env_int("MMRS_DENSE_TILES", -1), a.d_keys,
-               a.g_world, a.g_rank, a.g_peer_bufs, a.g_peer_flags, a.g_list_stride, knob_hash()};
-  cudaGraphExec_t exec = nullptr;
-  long long kernels = 0;
-  {
-    std::lock_guard<std::mutex> lk(g_graph_mu);
-    for (GraphEntry& e : g_graphs)
-      if (e.key == key) { e.stamp = ++g_graph_clock; exec = e.exec; kernels = e.kernels; break; }
+  GraphKey key{a.gallery, a.n_rows, a.dim, a.ld, a.dtype, a.n_queries, a.ldq_in, a.k,
+               a.normalize, a.scale, a.index_offset, a.path, workspace,
+               dev.device, env_int("MMRS_RATIO_LOG2", -1), env_int("MMRS_DENSE_TILES", -1),
+               a.d_values != nullptr, a.d_indices != nullptr, a.d_keys != nullptr,
+               a.g_world, a.g_rank, a.g_peer_bufs, a.g_peer_flags, a.g_local_buf, a.g_local_flags, a.g_list_stride,
+               a.g_k_out, a.g_timeout_ns, knob_hash()};
+  // the lock is held across patch + launch: an executable graph must not be updated or launched from
+  // two threads at once (two threads sharing one workspace would be a caller bug anyway)
+  std::lock_guard<std::mutex> lk(g_graph_mu);
+  GraphEntry* hit = nullptr;
+  for (GraphEntry& e : g_graphs) {
+    if (!(e.key == key)) continue;
+    const bool same = e.q == a.d_queries && e.v == a.d_values && e.i == a.d_indices && e.keys == a.d_keys;
+    if (same || e.patchable) { hit = &e; break; }
   }
-  if (exec) {
-    g_launches.fetch_add(kernels);   // a replay launches the same kernels the capture recorded
-  } else {
-    cudaGraph_t graph = nullptr;
-    const long long before = g_launches.load();
-    // capture on a private stream: the caller's may be the legacy default stream, which cannot
-    // capture; the instantiated graph is then launched into the caller's stream
-    static thread_local cudaStream_t cap_stream[64] = {};
-    if (!cap_stream[dev.device])
-      MMRS_CUDA(cudaStreamCreateWithFlags(&cap_stream[dev.device], cudaStreamNonBlocking));
-    cudaStream_t cs = cap_stream[dev.device];
-    MMRS_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-    const int rc = enqueue_search(a, dev, w, cs);
-    kernels = g_launches.load() - before;
-    const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
-    if (rc != MMRS_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
-    if (ce != cudaSuccess) return fail(MMRS_ERR_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(ce));
-    const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
-    cudaGraphDestroy(graph);
-    if (ie != cudaSuccess) return fail(MMRS_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
-    std::lock_guard<std::mutex> lk(g_graph_mu);
-    if (g_graphs.size() >= kMaxGraphs) {   // evict the least recently used
-      size_t victim = 0;
-      for (size_t i = 1; i < g_graphs.size(); ++i)
-        if (g_graphs[i].stamp < g_graphs[victim].stamp) victim = i;
-      cudaGraphExecDestroy(g_graphs[victim].exec);
-      g_graphs.erase(g_graphs.begin() + victim);
+  if (hit) {
+    hit->stamp = ++g_graph_clock;
+    if (!(hit->q == a.d_queries && hit->v == a.d_values && hit->i == a.d_indices && hit->keys == a.d_keys)) {
+      int rc = patch_entry(*hit, a);
+      if (rc != MMRS_OK) return rc;
     }
-    g_graphs.push_back(GraphEntry{key, exec, ++g_graph_clock, kernels});
+    g_launches.fetch_add(hit->kernels);   // a replay launches the same kernels the capture recorded
+    g_stat_replays.fetch_add(1);
+    MMRS_CUDA(cudaGraphLaunch(hit->exec, stream));
+    return MMRS_OK;
   }
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  const long long before = g_launches.load();
+  // capture on a private stream: the caller's may be the legacy default stream, which cannot
+  // capture; the instantiated graph is then launched into the caller's stream
+  static thread_local cudaStream_t cap_stream[64] = {};
+  if (!cap_stream[dev.device])
+    MMRS_CUDA(cudaStreamCreateWithFlags(&cap_stream[dev.device], cudaStreamNonBlocking));
+  cudaStream_t cs = cap_stream[dev.device];
+  MMRS_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+  const int rc = enqueue_search(a, dev, w, cs);
+  const long long kernels = g_launches.load() - before;
+  const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+  if (rc != MMRS_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+  if (ce != cudaSuccess) return fail(MMRS_ERR_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(ce));
+  const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+  if (ie != cudaSuccess) {
+    cudaGraphDestroy(graph);
+    return fail(MMRS_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
+  }
+  GraphEntry e{key, graph, exec, ++g_graph_clock, kernels, {}, false, a.d_queries, a.d_values, a.d_indices, a.d_keys};
+  e.patchable = discover_sites(graph, a, &e.sites);   // the graph is kept: its nodes own the parameter storage
+  if (!e.patchable) { e.sites.clear(); g_stat_unpatchable.fetch_add(1); }
+  g_stat_captures.fetch_add(1);
+  if (g_graphs.size() >= kMaxGraphs) {   // evict the least recently used
+    size_t victim = 0;
+    for (size_t i = 1; i < g_graphs.size(); ++i)
+      if (g_graphs[i].stamp < g_graphs[victim].stamp) victim = i;
+    cudaGraphExecDestroy(g_graphs[victim].exec);
+    cudaGraphDestroy(g_graphs[victim].graph);
+    g_graphs.erase(g_graphs.begin() + victim);
+  }
+  g_graphs.push_back(e);
   MMRS_CUDA(cudaGraphLaunch(exec, stream));
   return MMRS_OK;
 }
@@ -505,6 +661,9 @@ static int launch_search_graph(const SearchArgs& a, const DeviceInfo& dev, const
 static int flags_to_status(int32_t f) {
   if (f & kFlagZeroNorm)
     return fail(MMRS_ERR_ZERO_NORM, "a query row has zero L2 norm and normalize_queries is set");
+  if (f & kFlagGatherTimeout)
+    return fail(MMRS_ERR_TIMEOUT, "fused all-gather: a peer rank did not deliver / acknowledge its top-k lists within "
+                "MMRS_GATHER_TIMEOUT_MS (a dead or diverged rank; results of this batch are invalid)");
   if (f & kFlagWatchdog) return fail(MMRS_ERR_INTERNAL, "K2 pipeline watchdog fired (mbarrier wait timed out)");
   if (f & kFlagShort) return fail(MMRS_ERR_INTERNAL, "select saw fewer than k unique candidates");
   if (f & kFlagOverflow) return fail(MMRS_ERR_INTERNAL, "candidate list overflow");
@@ -582,7 +741,7 @@ int mmrs_full_scores(const void* d_gallery, int64_t n_rows, int32_t dim, int64_t
   MMRS_CUDA(cudaMemsetAsync(w.flags, 0, 8 * sizeof(int32_t), stream));
   MMRS_LAUNCH(launch_prep_queries(d_queries, n_queries, ld_queries, dim, normalize_queries,
                                 gallery_dtype == MMRS_DTYPE_BF16 ? 1 : (gallery_dtype == MMRS_DTYPE_BF16X3 ? 2 : 0),
-                                w.q_f32, w.q_bf16, qp, ldq, w.flags, stream));
+                                w.q_f32, w.q_bf16, qp, ldq, w.flags, GatherPrologue{}, stream));
   ScanParams base{};
   base.gallery = d_gallery; base.n_rows = n_rows; base.ld = ld_gallery; base.dim = dim;
   base.queries = w.q_f32; base.ldq = ldq; base.scale = scale;
@@ -675,29 +834,45 @@ static int search_common(SearchArgs a, const float* h_queries, float* h_values, 
                          void* d_workspace, size_t workspace_bytes, cudaStream_t stream) {
   int32_t* h = pinned_status();
   if (!h) return fail(MMRS_ERR_CUDA, "cudaHostAlloc for the status word failed");
-  DeviceInfo dev;
-  Workspace w{};
-  int rc = search_enqueue(a, h_queries, h_values, h_indices, d_workspace, workspace_bytes, h, stream, &dev, &w);
+  int rc = search_enqueue(a, h_queries, h_values, h_indices, d_workspace, workspace_bytes, h, stream, nullptr, nullptr);
   if (rc != MMRS_OK || a.n_queries == 0) return rc;
-  const bool host_io = h_queries != nullptr;
-  const size_t vbytes = static_cast<size_t>(a.n_queries) * a.k * sizeof(float);
-  const size_t ibytes = static_cast<size_t>(a.n_queries) * a.k * sizeof(int64_t);
   MMRS_CUDA(cudaStreamSynchronize(stream));
-  int32_t f = h[0];
-  if (f == kFlagOverflow) {
-    // exact but slow: rerun every query exhaustively (rare: needs scores correlated with the
-    // tile stride pattern)
-    rc = enqueue_exhaustive(a, dev, w, stream);
-    if (rc != MMRS_OK) return rc;
-    MMRS_CUDA(cudaMemcpyAsync(h, w.flags, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
-    if (host_io) {
-      MMRS_CUDA(cudaMemcpyAsync(h_values, a.d_values, vbytes, cudaMemcpyDeviceToHost, stream));
-      MMRS_CUDA(cudaMemcpyAsync(h_indices, a.d_indices, ibytes, cudaMemcpyDeviceToHost, stream));
-    }
-    MMRS_CUDA(cudaStreamSynchronize(stream));
-    f = h[0];
-  }
-  return flags_to_status(f);
+  return mmrs_search_status(h);   // MMRS_ERR_RETRY on a candidate-list overflow: mmrs_search_topk_exhaustive
+}
+
+size_t mmrs_search_exhaustive_workspace_bytes(int64_t n_rows, int32_t dim, int32_t n_queries) {
+  if (n_rows < 1 || dim < 1 || n_queries < 1) return 0;
+  return carve(nullptr, n_rows, dim, n_queries, 1, true, true).total;
+}
+
+int mmrs_search_topk_exhaustive(const void* d_gallery, int64_t n_rows, int32_t dim, int64_t ld_gallery,
+                                int32_t gallery_dtype, const float* d_queries, int32_t n_queries,
+                                int64_t ld_queries, int32_t k, int32_t normalize_queries, float scale,
+                                int64_t index_offset, float* d_out_values, int64_t* d_out_indices,
+                                void* d_workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceInfo dev;
+  int rc = current_device(&dev);
+  if (rc != MMRS_OK) return rc;
+  rc = check_matrix(d_gallery, n_rows, dim, ld_gallery, gallery_dtype, "gallery");
+  if (rc != MMRS_OK) return rc;
+  if (n_queries == 0) return MMRS_OK;
+  if (n_queries < 0 || !d_queries || !d_out_values || !d_out_indices || ld_queries < dim)
+    return fail(MMRS_ERR_ARG, "bad query / output arguments");
+  if (k < 1 || k > 1024 || k > n_rows) return fail(MMRS_ERR_ARG, "k = %d must be in [1, min(1024, n_rows)]", k);
+  const size_t need = mmrs_search_exhaustive_workspace_bytes(n_rows, dim, n_queries);
+  if (!d_workspace || workspace_bytes < need || reinterpret_cast<uintptr_t>(d_workspace) % 256)
+    return fail(MMRS_ERR_WORKSPACE, "workspace %zu bytes, need %zu (256-byte aligned)", workspace_bytes, need);
+  const Workspace w = carve(d_workspace, n_rows, dim, n_queries, 1, true, true);
+  SearchArgs a{d_gallery, n_rows, dim, ld_gallery, gallery_dtype, d_queries, n_queries, ld_queries,
+               k, normalize_queries, scale, index_offset, MMRS_PATH_AUTO, d_out_values, d_out_indices};
+  rc = enqueue_exhaustive(a, dev, w, stream);
+  if (rc != MMRS_OK) return rc;
+  int32_t* h = pinned_status();
+  if (!h) return fail(MMRS_ERR_CUDA, "cudaHostAlloc for the status word failed");
+  MMRS_CUDA(cudaMemcpyAsync(h, w.flags, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  MMRS_CUDA(cudaStreamSynchronize(stream));
+  return flags_to_status(h[0]);
 }
 
 int mmrs_search_topk(const void* d_gallery, int64_t n_rows, int32_t dim, int64_t ld_gallery,
@@ -812,11 +987,12 @@ int mmrs_search_topk_fused_gather_async(const void* d_gallery, int64_t n_rows, i
                                         int64_t ld_queries, int32_t k_local, int32_t k_out,
                                         int32_t normalize_queries, float scale, int64_t index_offset, int32_t path,
                                         uint64_t* const* d_peer_bufs, uint32_t* const* d_peer_flags,
-                                        uint64_t* d_local_buf, int32_t rank, int32_t world, int64_t list_stride,
-                                        uint32_t epoch, float* d_out_values, int64_t* d_out_indices,
+                                        uint64_t* d_local_buf, uint32_t* d_local_flags, int32_t rank, int32_t world,
+                                        int64_t list_stride, float* d_out_values, int64_t* d_out_indices,
                                         void* d_workspace, size_t workspace_bytes, int32_t* h_status, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (world < 1 || world > 64 || rank < 0 || rank >= world || !d_peer_bufs || !d_peer_flags || !d_local_buf)
+  if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world || !d_peer_bufs || !d_peer_flags || !d_local_buf ||
+      !d_local_flags)
     return fail(MMRS_ERR_ARG, "bad rank / world / peer pointers");
   if (n_queries < 1 || n_queries > kSuperChunk)
     return fail(MMRS_ERR_ARG, "fused gather handles 1..%d queries per call", kSuperChunk);
@@ -826,43 +1002,21 @@ int mmrs_search_topk_fused_gather_async(const void* d_gallery, int64_t n_rows, i
     return fail(MMRS_ERR_ARG, "list_stride must be at least n_queries * k_local + 1");
   if (index_offset < 0 || index_offset + n_rows > 0x100000000ll)
     return fail(MMRS_ERR_ARG, "global row ids must fit 32 bits");
-  if (epoch == 0) return fail(MMRS_ERR_ARG, "epochs start at 1");
   if (!d_out_values || !d_out_indices || !h_status) return fail(MMRS_ERR_ARG, "null output pointer");
   SearchArgs a{d_gallery, n_rows, dim, ld_gallery, gallery_dtype, d_queries, n_queries, ld_queries,
-               k_local, normalize_queries, scale, index_offset, path, nullptr, nullptr};
+               k_local, normalize_queries, scale, index_offset, path, d_out_values, d_out_indices};
   a.g_world = world; a.g_rank = rank; a.g_peer_bufs = d_peer_bufs; a.g_peer_flags = d_peer_flags;
-  a.g_list_stride = list_stride;
-  // the epoch has to be on the device before the graph's producer select reads it
-  {
-    DeviceInfo dev0;
-    int rc0 = current_device(&dev0);
-    if (rc0 != MMRS_OK) return rc0;
-    const size_t need = mmrs_search_workspace_bytes(n_rows, dim, gallery_dtype, n_queries, k_local);
-    if (!d_workspace || workspace_bytes < need) return fail(MMRS_ERR_WORKSPACE, "workspace %zu bytes, need %zu", workspace_bytes, need);
-  }
-  const Workspace w0 = carve(d_workspace, n_rows, dim, n_queries, k_local, true);
-  MMRS_CUDA(cudaMemsetAsync(w0.gscratch, 0, 8 * sizeof(uint32_t), stream));   // counters, merge status
-  MMRS_LAUNCH(launch_fill_u32(w0.gscratch, epoch, 1, stream));
+  a.g_local_buf = d_local_buf; a.g_local_flags = d_local_flags;
+  a.g_list_stride = list_stride; a.g_k_out = k_out; a.g_timeout_ns = gather_timeout_ns();
+  for (int r = 0; r <= world + 1; ++r) h_status[r] = 0;
   Workspace w{};
+  // ONE graph: prep (epoch bump + ack wait) -> scans / selects -> producer select -> wait -> merge select
   int rc = search_enqueue(a, nullptr, nullptr, nullptr, d_workspace, workspace_bytes, h_status + world + 1, stream,
                           nullptr, &w);
   if (rc != MMRS_OK) return rc;
-  // consumer: merge the lists every rank stored into MY gather buffer, as soon as all have arrived
-  SelectParams sp{};
-  sp.cand = d_local_buf;
-  sp.cap = world * k_local; sp.fixed_n = world * k_local; sp.k = k_out; sp.final_pass = 1;
-  sp.out_values = d_out_values; sp.out_indices = d_out_indices; sp.index_offset = 0;
-  sp.flags = reinterpret_cast<int32_t*>(w.gscratch + 4);
-  sp.seg_len = k_local; sp.seg_stride = list_stride;
-  sp.g_role = 2; sp.g_world = world; sp.g_rank = rank; sp.g_peer_bufs = d_peer_bufs; sp.g_peer_flags = d_peer_flags;
-  sp.g_list_stride = list_stride; sp.g_status_index = n_queries * k_local;
-  sp.g_epoch = w.gscratch; sp.g_counter = w.gscratch + 2;
-  MMRS_LAUNCH(launch_select(sp, n_queries, stream));
-  // every rank's status word (gathered with its keys) and the merge's own flags
-  MMRS_CUDA(cudaMemcpy2DAsync(h_status, sizeof(int32_t), d_local_buf + static_cast<int64_t>(n_queries) * k_local,
-                              static_cast<size_t>(list_stride) * sizeof(uint64_t), sizeof(int32_t), world,
-                              cudaMemcpyDeviceToHost, stream));
-  MMRS_CUDA(cudaMemcpyAsync(h_status + world, w.gscratch + 4, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  // every rank's status word (the merge select's private snapshot) and the merge's own flags
+  MMRS_CUDA(cudaMemcpyAsync(h_status, w.gscratch + kGStatus, static_cast<size_t>(world + 1) * sizeof(int32_t),
+                            cudaMemcpyDeviceToHost, stream));
   return MMRS_OK;
 }
 
@@ -925,7 +1079,7 @@ int mmrs_topk_merge(const float* d_values_in, const int64_t* d_indices_in, int32
 
 size_t mmrs_selfjoin_workspace_bytes(int64_t n_rows, int32_t dim, int32_t dtype) {
   (void)n_rows; (void)dim; (void)dtype;
-  return 256;
+  return 0;   // the exact-mode join keeps everything in registers / shared memory: d_workspace may be NULL
 }
 
 int mmrs_selfjoin_pairs(const void* d_emb, int64_t n_rows, int32_t dim, int64_t ld_emb,
@@ -961,6 +1115,43 @@ int mmrs_selfjoin_pairs(const void* d_emb, int64_t n_rows, int32_t dim, int64_t 
 }
 
 int64_t mmrs_launch_count(void) { return g_launches.load(); }
+
+int mmrs_graph_stats(int64_t* h_out4) {
+  if (!h_out4) return fail(MMRS_ERR_ARG, "null pointer");
+  h_out4[0] = g_stat_captures.load(); h_out4[1] = g_stat_replays.load();
+  h_out4[2] = g_stat_patches.load(); h_out4[3] = g_stat_unpatchable.load();
+  return MMRS_OK;
+}
+
+size_t mmrs_sort_pairs_workspace_bytes(int64_t n_pairs) {
+  if (n_pairs < 1) n_pairs = 1;
+  int64_t m = 1;
+  while (m < n_pairs) m <<= 1;
+  return static_cast<size_t>(m) * sizeof(uint64_t);
+}
+
+int mmrs_sort_pairs(int64_t* d_pairs, int64_t n_pairs, void* d_workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceInfo dev;
+  int rc = current_device(&dev);
+  if (rc != MMRS_OK) return rc;
+  if (n_pairs < 0 || (n_pairs > 0 && !d_pairs)) return fail(MMRS_ERR_ARG, "bad arguments");
+  if (n_pairs < 2) return MMRS_OK;
+  if (!d_workspace || workspace_bytes < mmrs_sort_pairs_workspace_bytes(n_pairs))
+    return fail(MMRS_ERR_WORKSPACE, "workspace too small");
+  MMRS_LAUNCH(launch_sort_pairs(d_pairs, n_pairs, static_cast<uint64_t*>(d_workspace), stream));
+  return MMRS_OK;
+}
+
+int mmrs_row_norm_range(const float* d_emb, int64_t n_rows, int32_t dim, int64_t ld, float* d_out_min_max, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceInfo dev;
+  int rc = current_device(&dev);
+  if (rc != MMRS_OK) return rc;
+  if (!d_emb || !d_out_min_max || n_rows < 1 || dim < 1 || ld < dim) return fail(MMRS_ERR_ARG, "bad arguments");
+  MMRS_LAUNCH(launch_row_norm_range(d_emb, n_rows, dim, ld, d_out_min_max, dev.sm_count, stream));
+  return MMRS_OK;
+}
 
 int mmrs_profile_enable(int on) {
   g_prof_on.store(on ? 1 : 0);
@@ -1075,6 +1266,24 @@ int mmrs_threshold_sweep(const float* d_pos, int64_t n_pos, const float* d_neg, 
   MMRS_LAUNCH(launch_threshold_sweep(d_pos, n_pos, d_neg, n_neg, d_thresholds, n_thresholds,
                                    d_out_counts, static_cast<unsigned long long*>(d_workspace),
                                    dev.sm_count, stream));
+  return MMRS_OK;
+}
+
+int mmrs_threshold_sweep_f64(const double* d_pos, int64_t n_pos, const double* d_neg, int64_t n_neg,
+                             const double* d_thresholds, int32_t n_thresholds, int64_t* d_out_counts,
+                             void* d_workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DeviceInfo dev;
+  int rc = current_device(&dev);
+  if (rc != MMRS_OK) return rc;
+  if (n_thresholds < 1 || n_thresholds > 4096) return fail(MMRS_ERR_ARG, "n_thresholds must be in [1, 4096]");
+  if (n_pos < 0 || n_neg < 0 || (n_pos > 0 && !d_pos) || (n_neg > 0 && !d_neg) || !d_thresholds || !d_out_counts)
+    return fail(MMRS_ERR_ARG, "bad arguments");
+  if (!d_workspace || workspace_bytes < mmrs_threshold_sweep_workspace_bytes(n_thresholds))
+    return fail(MMRS_ERR_WORKSPACE, "workspace too small");
+  MMRS_LAUNCH(launch_threshold_sweep_f64(d_pos, n_pos, d_neg, n_neg, d_thresholds, n_thresholds,
+                                       d_out_counts, static_cast<unsigned long long*>(d_workspace),
+                                       dev.sm_count, stream));
   return MMRS_OK;
 }
 

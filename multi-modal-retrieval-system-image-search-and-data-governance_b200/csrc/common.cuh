@@ -215,7 +215,6 @@ constexpr int kPrepKernelParams = 12;
 const void* select_kernel_handle();
 cudaError_t launch_gather_wait(const uint32_t* my_flags, int32_t world, const uint32_t* epoch, int32_t* status,
                                uint64_t timeout_ns, cudaStream_t stream);
-cudaError_t launch_sort_u64(uint64_t* keys, uint64_t* scratch, int64_t n, cudaStream_t stream);
 cudaError_t launch_row_norm_range(const float* x, int64_t n_rows, int32_t dim, int64_t ld, float* out_min_max,
                                   int sm_count, cudaStream_t stream);
 cudaError_t launch_scan_gemv(const ScanParams& p, int32_t dtype, int mode, int sm_count,

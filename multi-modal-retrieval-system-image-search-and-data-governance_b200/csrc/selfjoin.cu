@@ -136,8 +136,9 @@ cudaError_t launch_selfjoin_f32(const float* emb, int64_t n_rows, int32_t dim, i
 // histogram bin, and a suffix sum turns the histogram into the counts.
 constexpr int kSweepMaxT = 4096;
 
-__global__ void __launch_bounds__(256) sweep_hist_kernel(const float* __restrict__ pos, int64_t n_pos,
-                                                         const float* __restrict__ neg, int64_t n_neg,
+template <typename S>   // float (numpy float32 scores) or double (float64 scores: no rounding on the way in)
+__global__ void __launch_bounds__(256) sweep_hist_kernel(const S* __restrict__ pos, int64_t n_pos,
+                                                         const S* __restrict__ neg, int64_t n_neg,
                                                          const double* __restrict__ thr, int32_t n_thr,
                                                          unsigned long long* __restrict__ hist) {
   extern __shared__ double s_thr[];                  // [n_thr]
@@ -246,9 +247,10 @@ __global__ void sweep_suffix_kernel(const unsigned long long* __restrict__ hist,
   }
 }
 
-cudaError_t launch_threshold_sweep(const float* pos, int64_t n_pos, const float* neg, int64_t n_neg,
-                                   const double* thr, int32_t n_thr, int64_t* out_counts,
-                                   unsigned long long* hist_ws, int sm_count, cudaStream_t stream) {
+template <typename S>
+static cudaError_t launch_threshold_sweep_t(const S* pos, int64_t n_pos, const S* neg, int64_t n_neg,
+                                            const double* thr, int32_t n_thr, int64_t* out_counts,
+                                            unsigned long long* hist_ws, int sm_count, cudaStream_t stream) {
   if (n_thr < 1 || n_thr > kSweepMaxT) return cudaErrorInvalidValue;
   cudaError_t e = cudaMemsetAsync(hist_ws, 0, sizeof(unsigned long long) * 2 * (n_thr + 1), stream);
   if (e != cudaSuccess) return e;
@@ -257,14 +259,24 @@ cudaError_t launch_threshold_sweep(const float* pos, int64_t n_pos, const float*
   int64_t grid = (total + 256 * 8 - 1) / (256 * 8);
   if (grid > sm_count * 4) grid = sm_count * 4;
   if (grid < 1) grid = 1;
-  e = cudaFuncSetAttribute(sweep_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  e = cudaFuncSetAttribute(sweep_hist_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            static_cast<int>(sizeof(double) * kSweepMaxT + sizeof(uint32_t) * 2 * (kSweepMaxT + 1)));
   if (e != cudaSuccess) return e;
-  sweep_hist_kernel<<<static_cast<int>(grid), 256, smem, stream>>>(pos, n_pos, neg, n_neg, thr, n_thr, hist_ws);
+  sweep_hist_kernel<S><<<static_cast<int>(grid), 256, smem, stream>>>(pos, n_pos, neg, n_neg, thr, n_thr, hist_ws);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   sweep_suffix_kernel<<<1, 32, 0, stream>>>(hist_ws, n_thr, out_counts);
   return cudaGetLastError();
+}
+cudaError_t launch_threshold_sweep(const float* pos, int64_t n_pos, const float* neg, int64_t n_neg,
+                                   const double* thr, int32_t n_thr, int64_t* out_counts,
+                                   unsigned long long* hist_ws, int sm_count, cudaStream_t stream) {
+  return launch_threshold_sweep_t<float>(pos, n_pos, neg, n_neg, thr, n_thr, out_counts, hist_ws, sm_count, stream);
+}
+cudaError_t launch_threshold_sweep_f64(const double* pos, int64_t n_pos, const double* neg, int64_t n_neg,
+                                       const double* thr, int32_t n_thr, int64_t* out_counts,
+                                       unsigned long long* hist_ws, int sm_count, cudaStream_t stream) {
+  return launch_threshold_sweep_t<double>(pos, n_pos, neg, n_neg, thr, n_thr, out_counts, hist_ws, sm_count, stream);
 }
 
 cudaError_t launch_threshold_sweep_labeled(const float* scores, const int64_t* targets, int64_t label, int64_t n,
@@ -290,6 +302,119 @@ cudaError_t launch_threshold_sweep_labeled(const float* scores, const int64_t* t
   sweep_hist_labeled_kernel<<<static_cast<int>(grid), 256, smem, stream>>>(scores, targets, label, n, thr_out, n_thr,
                                                                             hist_ws);
   sweep_suffix_kernel<<<1, 32, 0, stream>>>(hist_ws, n_thr, out_counts);
+  return cudaGetLastError();
+}
+
+// ---- lexicographic sort of the emitted pairs ----------------------------------------------------------------
+// The join kernels append pairs in whatever order their CTAs finish; `triu(S >= tau, 1).nonzero()` of the
+// oracle is row-major, i.e. sorted by (i, j).  Pairs are packed into u64 keys (i << 32 | j; row ids fit 32
+// bits) and sorted with a bitonic network: sub-sequences of 2048 keys in shared memory, larger strides
+// as one pass over global memory each.  O(n log^2 n) -- the pair list is tiny next to the join itself.
+constexpr int kSortBlock = 1024;           // threads; one block sorts 2 * kSortBlock keys in shared memory
+constexpr int kSortTile = 2 * kSortBlock;
+
+__global__ void pack_pairs_kernel(const int64_t* __restrict__ pairs, int64_t n, uint64_t* __restrict__ keys, int64_t m) {
+  const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (t >= m) return;
+  keys[t] = t < n ? (static_cast<uint64_t>(pairs[2 * t]) << 32) | static_cast<uint64_t>(pairs[2 * t + 1] & 0xffffffffll)
+                  : ~0ull;   // padding sorts to the end
+}
+__global__ void unpack_pairs_kernel(const uint64_t* __restrict__ keys, int64_t n, int64_t* __restrict__ pairs) {
+  const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (t >= n) return;
+  pairs[2 * t] = static_cast<int64_t>(keys[t] >> 32);
+  pairs[2 * t + 1] = static_cast<int64_t>(keys[t] & 0xffffffffull);
+}
+__device__ __forceinline__ void cmp_swap(uint64_t& a, uint64_t& b, bool ascending) {
+  if ((a > b) == ascending) { const uint64_t t = a; a = b; b = t; }
+}
+// all steps (k, j) with j < kSortTile of the stages k_lo..k_hi for this block's 2048 keys
+__global__ void __launch_bounds__(kSortBlock) bitonic_smem_kernel(uint64_t* __restrict__ keys, int64_t k_lo, int64_t k_hi) {
+  __shared__ uint64_t s[kSortTile];
+  const int64_t base = static_cast<int64_t>(blockIdx.x) * kSortTile;
+  s[threadIdx.x] = keys[base + threadIdx.x];
+  s[threadIdx.x + kSortBlock] = keys[base + threadIdx.x + kSortBlock];
+  __syncthreads();
+  for (int64_t k = k_lo; k <= k_hi; k <<= 1) {
+    for (int64_t j = (k >> 1) < kSortBlock ? (k >> 1) : kSortBlock; j > 0; j >>= 1) {
+      // thread t handles the pair (lo, lo + j) with lo = index whose bit j is clear
+      const int64_t t = threadIdx.x;
+      const int64_t lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+      const bool ascending = ((base + lo) & k) == 0;
+      cmp_swap(s[lo], s[lo + j], ascending);
+      __syncthreads();
+    }
+  }
+  keys[base + threadIdx.x] = s[threadIdx.x];
+  keys[base + threadIdx.x + kSortBlock] = s[threadIdx.x + kSortBlock];
+}
+__global__ void bitonic_global_kernel(uint64_t* __restrict__ keys, int64_t m, int64_t k, int64_t j) {
+  const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (t >= (m >> 1)) return;
+  const int64_t lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+  uint64_t a = keys[lo], b = keys[lo + j];
+  const bool ascending = (lo & k) == 0;
+  if ((a > b) == ascending) { keys[lo] = b; keys[lo + j] = a; }
+}
+
+cudaError_t launch_sort_pairs(int64_t* pairs, int64_t n_pairs, uint64_t* scratch, cudaStream_t stream) {
+  if (n_pairs < 2) return cudaSuccess;
+  int64_t m = kSortTile;
+  while (m < n_pairs) m <<= 1;
+  // the workspace holds the power of two >= n_pairs; below one tile only that many keys exist: sort a
+  // full tile's worth in shared memory from a smaller buffer by clamping the tile to m0
+  int64_t m0 = 1;
+  while (m0 < n_pairs) m0 <<= 1;
+  if (m0 < kSortTile) {
+    // small lists: single-block global passes are enough (at most 11 * 12 / 2 tiny launches)
+    pack_pairs_kernel<<<static_cast<int>((m0 + 255) / 256), 256, 0, stream>>>(pairs, n_pairs, scratch, m0);
+    for (int64_t k = 2; k <= m0; k <<= 1)
+      for (int64_t j = k >> 1; j > 0; j >>= 1)
+        bitonic_global_kernel<<<static_cast<int>(((m0 >> 1) + 255) / 256), 256, 0, stream>>>(scratch, m0, k, j);
+    unpack_pairs_kernel<<<static_cast<int>((n_pairs + 255) / 256), 256, 0, stream>>>(scratch, n_pairs, pairs);
+    return cudaGetLastError();
+  }
+  m = m0;
+  const int tiles = static_cast<int>(m / kSortTile);
+  pack_pairs_kernel<<<static_cast<int>((m + 255) / 256), 256, 0, stream>>>(pairs, n_pairs, scratch, m);
+  bitonic_smem_kernel<<<tiles, kSortBlock, 0, stream>>>(scratch, 2, kSortTile);
+  for (int64_t k = 2 * kSortTile; k <= m; k <<= 1) {
+    for (int64_t j = k >> 1; j >= kSortTile; j >>= 1)
+      bitonic_global_kernel<<<static_cast<int>(((m >> 1) + 255) / 256), 256, 0, stream>>>(scratch, m, k, j);
+    bitonic_smem_kernel<<<tiles, kSortBlock, 0, stream>>>(scratch, k, k);
+  }
+  unpack_pairs_kernel<<<static_cast<int>((n_pairs + 255) / 256), 256, 0, stream>>>(scratch, n_pairs, pairs);
+  return cudaGetLastError();
+}
+
+// ---- range of the row norms (guard of the bf16 prefilter margin, which assumes unit rows) -------------------
+__global__ void __launch_bounds__(256) row_norm_range_kernel(const float* __restrict__ x, int64_t n_rows, int32_t dim,
+                                                             int64_t ld, uint32_t* __restrict__ mm) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+  uint32_t lo = 0xffffffffu, hi = 0u;
+  for (int64_t r = blockIdx.x * static_cast<int64_t>(blockDim.x >> 5) + (threadIdx.x >> 5); r < n_rows; r += warps) {
+    const float* row = x + r * ld;
+    float ss = 0.f;
+    for (int d = lane; d < dim; d += 32) ss = fmaf(row[d], row[d], ss);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const uint32_t bits = __float_as_uint(sqrtf(ss));     // norms are >= 0: bit order == value order
+    lo = bits < lo ? bits : lo;
+    hi = bits > hi ? bits : hi;
+  }
+  if (lane == 0 && lo != 0xffffffffu) { atomicMin(mm, lo); atomicMax(mm + 1, hi); }
+}
+cudaError_t launch_row_norm_range(const float* x, int64_t n_rows, int32_t dim, int64_t ld, float* out_min_max,
+                                  int sm_count, cudaStream_t stream) {
+  uint32_t* mm = reinterpret_cast<uint32_t*>(out_min_max);
+  cudaError_t e = cudaMemsetAsync(mm, 0xff, sizeof(uint32_t), stream);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(mm + 1, 0, sizeof(uint32_t), stream);
+  if (e != cudaSuccess) return e;
+  int64_t grid = (n_rows + 7) / 8;
+  if (grid > static_cast<int64_t>(sm_count) * 8) grid = static_cast<int64_t>(sm_count) * 8;
+  row_norm_range_kernel<<<static_cast<int>(grid), 256, 0, stream>>>(x, n_rows, dim, ld, mm);
   return cudaGetLastError();
 }
 

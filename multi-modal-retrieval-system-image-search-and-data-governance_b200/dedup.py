@@ -51,13 +51,11 @@ def selfjoin_raw(x: torch.Tensor, threshold: float, row_begin: int = 0, row_end:
     cap = int(capacity) if capacity is not None else max(4096, 2 * (row_end - row_begin))
     with torch.cuda.device(x.device):
         count = torch.zeros(1, dtype=torch.int64, device=x.device)
-        ws = torch.empty(512, dtype=torch.uint8, device=x.device)
         while True:
             pairs = torch.empty((cap, 2), dtype=torch.int64, device=x.device)
             st = lib.mmrs_selfjoin_pairs(x.data_ptr(), n, int(x.shape[1]), x.stride(0), _cabi.DTYPE_F32,
                                          float(threshold), int(row_begin), row_end, pairs.data_ptr(),
-                                         cap, count.data_ptr(), DeviceGallery.aligned_ptr(ws), 256,
-                                         _stream_handle(x.device))
+                                         cap, count.data_ptr(), None, 0, _stream_handle(x.device))
             found = int(count.item())
             if st == _cabi.ERR_CAPACITY:
                 cap = found  # exact size is known now
@@ -69,14 +67,31 @@ def selfjoin_raw(x: torch.Tensor, threshold: float, row_begin: int = 0, row_end:
 BF16_MARGIN = 0.0045   # > 2 * 2^-9 * (1 + 2^-9): bound on the bf16 rounding of a unit-norm dot product
 
 
+def row_norm_range(x32: torch.Tensor) -> "tuple[float, float]":
+    """(min, max) L2 norm over the rows of a device fp32 matrix (mmrs_row_norm_range)."""
+    with torch.cuda.device(x32.device):
+        mm = torch.empty(2, dtype=torch.float32, device=x32.device)
+        _cabi.check(_cabi.lib.mmrs_row_norm_range(x32.data_ptr(), int(x32.shape[0]), int(x32.shape[1]), x32.stride(0),
+                                                  mm.data_ptr(), _stream_handle(x32.device)))
+        lo, hi = mm.tolist()
+    return float(lo), float(hi)
+
+
 def selfjoin_tc_raw(x32: torch.Tensor, threshold: float, rank: int = 0, world: int = 1,
                     x16: Optional[torch.Tensor] = None, margin: float = BF16_MARGIN,
                     capacity: Optional[int] = None) -> torch.Tensor:
     """Unsorted int64 [P, 2] pairs of rank `rank`'s panels: tcgen05 bf16 prefilter at
-    threshold - margin, exact fp32 recheck (mmrs_selfjoin_pairs_tc); buffers grow on demand."""
+    threshold - margin, exact fp32 recheck (mmrs_selfjoin_pairs_tc); buffers grow on demand.
+    `margin` bounds the bf16 rounding error of a dot product of UNIT rows; it is scaled by the
+    largest squared row norm found on the device (|<a,b> - <a16,b16>| <= ~2^-8 |a||b|), so rows that
+    are not unit-norm (raw CLIP features) cannot lose true pairs before the exact recheck."""
     n, d = int(x32.shape[0]), int(x32.shape[1])
     lib = _cabi.lib
     dev = x32.device
+    _, max_norm = row_norm_range(x32)
+    if not (max_norm < float("inf")):
+        raise ValueError("embeddings contain non-finite rows")
+    margin = float(margin) * max(1.0, max_norm * max_norm * 1.0001)
     if x16 is None:
         x16 = x32.to(torch.bfloat16)
     cap = int(capacity) if capacity is not None else max(4096, n // 4)
@@ -102,11 +117,23 @@ def selfjoin_tc_raw(x32: torch.Tensor, threshold: float, rank: int = 0, world: i
 
 
 def sort_pairs(pairs: torch.Tensor, n: int) -> torch.Tensor:
-    """Lexicographic (i, j) order -- what `triu(S >= tau, 1).nonzero()` yields row-major."""
+    """Lexicographic (i, j) order -- what `triu(S >= tau, 1).nonzero()` yields row-major.
+    Device pair lists are sorted by the library's own bitonic sort on packed (i << 32 | j) keys
+    (mmrs_sort_pairs); host lists (CPU tests of the sharded protocol) by numpy."""
+    del n
     if pairs.numel() == 0:
         return pairs.reshape(0, 2)
-    key = pairs[:, 0] * int(n) + pairs[:, 1]
-    return pairs[torch.argsort(key)].contiguous()
+    if not pairs.is_cuda:
+        a = pairs.numpy()
+        return torch.from_numpy(a[np.lexsort((a[:, 1], a[:, 0]))].copy())
+    out = pairs.contiguous().clone()
+    lib = _cabi.lib
+    with torch.cuda.device(out.device):
+        ws_bytes = lib.mmrs_sort_pairs_workspace_bytes(int(out.shape[0]))
+        ws = torch.empty(int(ws_bytes) + 256, dtype=torch.uint8, device=out.device)
+        _cabi.check(lib.mmrs_sort_pairs(out.data_ptr(), int(out.shape[0]), DeviceGallery.aligned_ptr(ws), ws_bytes,
+                                        _stream_handle(out.device)))
+    return out
 
 
 def find_duplicate_pairs(emb, threshold: float, *, device=None, method: str = "auto") -> torch.Tensor:
@@ -203,14 +230,41 @@ def _remove(path: str, dry_run: bool) -> bool:
         return False
 
 
-def _cross_folder(reference_folder, delete_folder, embed: Embedder, threshold: float, dry_run: bool):
+def calculate_image_hash(image_path):
+    """Drop-in for tool/find_repeated.py:6-19: MD5 of the RGB pixel bytes (None for unreadable files)."""
+    import hashlib
+    from PIL import Image
+    try:
+        with Image.open(image_path) as img:
+            return hashlib.md5(img.convert("RGB").tobytes()).hexdigest()
+    except Exception as e:  # noqa: BLE001 -- mirror the reference's blanket handler
+        print(f"Error processing {image_path}: {e}")
+        return None
+
+
+def _check_cosine_threshold(t, what: str) -> float:
+    """Thresholds of the destructive wrappers must be cosines in (0.5, 1]."""
+    if isinstance(t, bool) or not isinstance(t, (int, float, np.floating, np.integer)):
+        raise TypeError(f"{what} must be a number in (0.5, 1], got {t!r}")
+    t = float(t)
+    if not (0.5 < t <= 1.0):
+        raise ValueError(f"{what} = {t!r}: this build's predicate is cos(e_i, e_j) >= threshold on unit-norm "
+                         "embeddings and accepts 0.5 < threshold <= 1 (higher = stricter); the reference's "
+                         "`similarity_threshold` is a Hamming radius on perceptual hashes (0 = strictest, default 5) "
+                         "and cannot be translated -- pass cosine_threshold=0.95 (or stricter) instead")
+    return t
+
+
+def _cross_folder(reference_folder, delete_folder, embed: Optional[Embedder], threshold: float, dry_run: bool,
+                  confirm: str):
     reference_images = get_all_images(reference_folder)
     delete_images = get_all_images(delete_folder)
     print(f"Found {len(reference_images)} images in reference folder")
     print(f"Found {len(delete_images)} images in delete folder")
     deleted_files, kept_files = [], []
-    ref_emb, ref_ok = embed(reference_images)
-    del_emb, del_ok = embed(delete_images)
+    embed_fn = embed or pixel_embedding
+    ref_emb, ref_ok = embed_fn(reference_images)
+    del_emb, del_ok = embed_fn(delete_images)
     ref_paths = [p for p, ok in zip(reference_images, ref_ok) if ok]
     match = {}
     if len(ref_paths) and del_emb.shape[0]:
@@ -222,6 +276,22 @@ def _cross_folder(reference_folder, delete_folder, embed: Embedder, threshold: f
         for row, (v, i) in enumerate(zip(vals, idx)):
             if v >= threshold:
                 match[delete_images[ok_pos[row]]] = ref_paths[int(i)]
+    if confirm == "exact" and match:
+        # The reference's predicate is pixel identity (MD5 of the RGB bytes, find_repeated.py:6-19).  The
+        # embedding search above is the prefilter (identical pixels -> identical vectors -> cos = 1, so it
+        # has no false negatives); a candidate is only deleted when its hash equals a reference image's, and
+        # the reported reference is the LAST one with that hash, as the reference's dict build leaves it (:50-52).
+        reference_hashes = {}
+        for p in reference_images:
+            h = calculate_image_hash(p)
+            if h:
+                reference_hashes[h] = p
+        confirmed = {}
+        for p in match:
+            h = calculate_image_hash(p)
+            if h and h in reference_hashes:
+                confirmed[p] = reference_hashes[h]
+        match = confirmed
     for img_path in delete_images:
         if img_path in match:
             if _remove(img_path, dry_run):
@@ -231,12 +301,14 @@ def _cross_folder(reference_folder, delete_folder, embed: Embedder, threshold: f
     return deleted_files, kept_files, len(reference_images), len(delete_images)
 
 
-def find_and_remove_near_duplicate_images(folder_path, similarity_threshold=0.95, *,
+def find_and_remove_near_duplicate_images(folder_path, cosine_threshold=0.95, *,
                                           embed: Optional[Embedder] = None, dry_run: bool = False):
     """Same-folder form, tool/find_repeated_in_same_folder.py:56-106: sort by file size descending
     (:73), keep the first of every group of similar images, delete the rest.
     Returns (deleted_files [(dup, original)], reference_images, total).
-    `similarity_threshold` is a cosine threshold here (the reference's is a Hamming radius)."""
+    The predicate is cos(e_i, e_j) >= `cosine_threshold` (0.5 < t <= 1) on the embeddings, where the
+    reference uses a Hamming radius on perceptual hashes."""
+    cosine_threshold = _check_cosine_threshold(cosine_threshold, "cosine_threshold")
     embed = embed or pixel_embedding
     all_images = get_all_images(folder_path)
     print(f"在文件夹中找到 {len(all_images)} 个图像")
@@ -245,7 +317,7 @@ def find_and_remove_near_duplicate_images(folder_path, similarity_threshold=0.95
     usable = [p for p, good in zip(all_images, ok) if good]   # unreadable files are skipped (:78)
     reference_images, duplicate_images = [], []
     if len(usable) >= 2:
-        pairs = find_duplicate_pairs(emb, similarity_threshold)
+        pairs = find_duplicate_pairs(emb, cosine_threshold)
         reps, dups = greedy_first_keeper(len(usable), pairs, range(len(usable)))
         reference_images = [usable[i] for i in reps]
         duplicate_images = [(usable[d], usable[o]) for d, o in dups]
@@ -256,19 +328,38 @@ def find_and_remove_near_duplicate_images(folder_path, similarity_threshold=0.95
 
 
 def find_and_remove_duplicate_images(reference_folder, delete_folder=None, *, embed: Optional[Embedder] = None,
-                                     threshold: float = 0.9999, dry_run: bool = False):
+                                     threshold: float = 0.9999, cosine_threshold: float = 0.95,
+                                     confirm: Optional[str] = None, dry_run: bool = False):
     """Drop-in for BOTH reference functions of this name.
 
-    (reference_folder, delete_folder: str)  -> tool/find_repeated.py:35-71
+    (reference_folder, delete_folder: path)  -> tool/find_repeated.py:35-71
         images of `delete_folder` that match an image of `reference_folder` are deleted;
-        returns (deleted_files [(path, ref_path)], kept_files, n_ref, n_del).
-    (folder_path, similarity_threshold: number | None) -> tool/find_repeated_in_same_folder.py:56-106
-        returns (deleted_files, reference_images, total).
+        returns (deleted_files [(path, ref_path)], kept_files, n_ref, n_del).  The GPU top-1 search
+        (cos >= `threshold`) finds the candidates; with the default embedder every candidate is then
+        CONFIRMED with the reference's own predicate -- equal MD5 of the RGB bytes -- before it is
+        deleted (`confirm="exact"`), so the deletion set and the reported reference paths are the
+        reference's.  A caller who passes an encoder (`embed=`) asks for the embedding predicate and gets
+        `confirm="none"` unless stated otherwise.
+    (folder_path) -> tool/find_repeated_in_same_folder.py:56-106
+        returns (deleted_files, reference_images, total); the predicate is cos >= `cosine_threshold`.
+        The reference's second positional argument is a Hamming radius (0 = strictest, default 5): a number
+        there is REFUSED with a ValueError -- it has no cosine equivalent, and guessing one on a function
+        that deletes files is not acceptable.
     """
-    if delete_folder is None or isinstance(delete_folder, (int, float)):
-        thr = 0.95 if delete_folder is None else float(delete_folder)
-        return find_and_remove_near_duplicate_images(reference_folder, thr, embed=embed, dry_run=dry_run)
-    return _cross_folder(reference_folder, delete_folder, embed or pixel_embedding, threshold, dry_run)
+    if delete_folder is None:
+        return find_and_remove_near_duplicate_images(reference_folder, cosine_threshold, embed=embed, dry_run=dry_run)
+    if not isinstance(delete_folder, (str, bytes, os.PathLike)):
+        raise ValueError(f"second argument {delete_folder!r}: a folder path selects the cross-folder form "
+                         "(tool/find_repeated.py); the same-folder form's `similarity_threshold` is a Hamming "
+                         "radius on perceptual hashes in the reference (0 = strictest, default 5), which this "
+                         "embedding-based build cannot honour -- call find_and_remove_duplicate_images(folder, "
+                         "cosine_threshold=0.95) with a cosine in (0.5, 1]")
+    threshold = _check_cosine_threshold(threshold, "threshold")
+    if confirm is None:
+        confirm = "exact" if embed is None else "none"
+    if confirm not in ("exact", "none"):
+        raise ValueError("confirm must be 'exact' or 'none'")
+    return _cross_folder(reference_folder, delete_folder, embed, threshold, dry_run, confirm)
 
 
 CROSS_SET_EXTENSIONS = ['.jpg', '.jpeg', '.png', '.bmp', '.gif', '.webp']   # tool/delete repeated.py:35
@@ -284,7 +375,11 @@ def detect_and_remove_cross_set_duplicates(test_dir, train_dir, hash_size=8, sim
     `hash_size` / `similarity_threshold` are the reference's dHash parameters and are accepted for
     signature compatibility; the predicate here is cos(e_train, e_test) >= `cosine_threshold`
     (top-1 search of the train embeddings against the test gallery)."""
-    del hash_size, similarity_threshold
+    del hash_size
+    if similarity_threshold != 0:
+        raise ValueError("similarity_threshold is the reference's dHash Hamming radius; only its default 0 (identical "
+                         "hashes) is accepted here -- the predicate of this build is cos >= cosine_threshold")
+    cosine_threshold = _check_cosine_threshold(cosine_threshold, "cosine_threshold")
     for d, name in ((test_dir, "测试集"), (train_dir, "训练集")):
         if not os.path.exists(d):
             print(f"错误: {name}目录 '{d}' 不存在。")

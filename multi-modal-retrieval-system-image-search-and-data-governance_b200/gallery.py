@@ -84,21 +84,31 @@ class DeviceGallery:
             self._workspaces[key] = buf
         return buf
 
-    def search_workspace(self, nq: int, k: int, host_io: bool, stream_id: int = 0):
-        """(aligned device pointer, byte size) of the scratch space of one search shape; sized by
-        the library's own query and cached, so a steady-state call allocates nothing.  One per
-        stream: searches in flight on different streams must not share candidate lists."""
+    MAX_SEARCH_SLOTS = 32      # LRU cap on cached search slots (a service with ever-changing batch sizes)
+
+    def search_slot(self, nq: int, k: int, host_io: bool, stream_id: int = 0) -> "SearchSlot":
+        """The slot of one search shape on one stream: device workspace (sized by the library's own
+        query, zero-filled once), pinned status words and events -- everything a steady-state call
+        needs, so that it allocates nothing.  One per stream: searches in flight on different
+        streams must not share candidate lists.  The library's CUDA-graph cache is keyed on the
+        slot's workspace, so one slot == one captured graph.  At most MAX_SEARCH_SLOTS are kept
+        (least recently used first out; the exhaustive fallback's 8-bytes-per-row buffer is NOT part
+        of a slot, it is allocated for the rare call that needs it)."""
         key = ("search", nq, k, host_io, stream_id)
-        hit = self._workspaces.get(key)
-        if hit is None:
-            lib = _cabi.lib
-            nbytes = lib.mmrs_search_workspace_bytes(self.n_rows, self.padded_dim, self.dtype_code, max(nq, 1), k)
-            if host_io:
-                nbytes += lib.mmrs_search_host_staging_bytes(self.padded_dim, max(nq, 1), k)
-            buf = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=self.device)
-            hit = (buf, self.aligned_ptr(buf), int(nbytes))
-            self._workspaces[key] = hit
-        return hit[1], hit[2]
+        slot = self._workspaces.pop(key, None)
+        if slot is None:
+            slots = [kk for kk in self._workspaces if isinstance(kk, tuple) and kk and kk[0] == "search"]
+            if len(slots) >= self.MAX_SEARCH_SLOTS:
+                torch.cuda.synchronize(self.device)       # the victim may still be in flight
+                del self._workspaces[slots[0]]            # dicts keep insertion order: [0] is the LRU
+            slot = SearchSlot(self, nq, k, host_io)
+        self._workspaces[key] = slot                      # (re)insert as most recently used
+        return slot
+
+    def search_workspace(self, nq: int, k: int, host_io: bool, stream_id: int = 0):
+        """(aligned device pointer, byte size) of the slot's workspace."""
+        slot = self.search_slot(nq, k, host_io, stream_id)
+        return slot.ptr, slot.nbytes
 
     @staticmethod
     def aligned_ptr(buf: torch.Tensor) -> int:
@@ -141,6 +151,40 @@ class DeviceGallery:
     def __repr__(self) -> str:
         return (f"DeviceGallery(rows={self.n_rows}, dim={self.dim}, mode={self.mode}, "
                 f"device={self.device}, row_offset={self.row_offset})")
+
+
+class SearchSlot:
+    """Buffers owned by one (gallery, n_queries, k, host_io, stream) search slot."""
+    N_STATUS = 16          # status words handed out round-robin to the batches in flight on the slot
+    STATUS_WORDS = 80      # int32 per status record (the fused gather reports world + 2 <= 66 words)
+
+    def __init__(self, gal: "DeviceGallery", nq: int, k: int, host_io: bool):
+        lib = _cabi.lib
+        nbytes = lib.mmrs_search_workspace_bytes(gal.n_rows, gal.padded_dim, gal.dtype_code, max(nq, 1), k)
+        if host_io:
+            nbytes += lib.mmrs_search_host_staging_bytes(gal.padded_dim, max(nq, 1), k)
+        self.buf = torch.zeros(int(nbytes) + 256, dtype=torch.uint8, device=gal.device)
+        self.ptr = DeviceGallery.aligned_ptr(self.buf)
+        self.nbytes = int(nbytes)
+        self.device = gal.device
+        self._status = torch.zeros((self.N_STATUS, self.STATUS_WORDS), dtype=torch.int32).pin_memory()
+        self._events = [torch.cuda.Event() for _ in range(self.N_STATUS)]
+        self._free = list(range(self.N_STATUS))
+        self.extra: dict = {}      # callers' per-slot state (e.g. the sharded search's device staging)
+
+    def acquire(self):
+        """-> (ticket, pinned status tensor [STATUS_WORDS] int32, event) for one batch in flight."""
+        if not self._free:         # every record is held by an unfinished (or dropped) handle: grow
+            n = self._status.shape[0]
+            self._status = torch.cat([self._status, torch.zeros_like(self._status)]).pin_memory()
+            self._events += [torch.cuda.Event() for _ in range(n)]
+            self._free = list(range(n, 2 * n))
+            self._grown = True
+        t = self._free.pop()
+        return t, self._status[t], self._events[t]
+
+    def release(self, ticket: int) -> None:
+        self._free.append(ticket)
 
 
 def load_feature_cache(path: str):

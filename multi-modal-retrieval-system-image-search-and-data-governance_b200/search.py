@@ -73,30 +73,54 @@ def _operand(gal: DeviceGallery, nq: int, path: str):
 class PendingSearch:
     """Handle of an asynchronous search (`search_topk(..., sync=False)`): `values` / `indices` are
     filled once the work enqueued on the stream has run; `wait()` blocks until then, checks the
-    batch's status word and returns `(values, indices)` (repeating the batch synchronously in the
-    rare case a candidate list overflowed)."""
+    batch's status word and returns `(values, indices)` (repeating the batch on the exhaustive path
+    in the rare case a candidate list overflowed)."""
 
-    def __init__(self, values, indices, status, event, redo):
+    def __init__(self, values, indices, slot, ticket, status, event, redo):
         self.values, self.indices = values, indices
-        self._status, self._event, self._redo = status, event, redo
-        self._done = False
+        self._slot, self._ticket, self._status, self._event, self._redo = slot, ticket, status, event, redo
+        self._done = slot is None
 
     def wait(self):
         if not self._done:
             self._event.synchronize()
             st = _cabi.lib.mmrs_search_status(self._status.data_ptr())
+            self._slot.release(self._ticket)      # only now may the status word serve another batch
+            self._done = True
             if st == _cabi.ERR_RETRY:
-                v, i = self._redo()
-                self.values.copy_(v)
-                self.indices.copy_(i)
+                self._redo(self.values, self.indices)
             else:
                 _cabi.check(st)
-            self._done = True
         return self.values, self.indices
 
 
+def _search_exhaustive(gal: DeviceGallery, q: torch.Tensor, k: int, normalize_queries: bool, scale: float,
+                       path: str, values: torch.Tensor, indices: torch.Tensor) -> None:
+    """The exact fallback for a batch whose candidate lists overflowed (MMRS_ERR_RETRY): every row a
+    key, one query at a time.  Its 8-bytes-per-row workspace lives only for this call."""
+    lib = _cabi.lib
+    dev = gal.device
+    nq = int(q.shape[0])
+    with torch.cuda.device(dev):
+        qd = q.to(dev) if not q.is_cuda else q
+        dv = values if values.is_cuda else torch.empty((nq, k), dtype=torch.float32, device=dev)
+        di = indices if indices.is_cuda else torch.empty((nq, k), dtype=torch.int64, device=dev)
+        g_ptr, g_ld, g_dtype = _operand(gal, nq, path)
+        ws_bytes = lib.mmrs_search_exhaustive_workspace_bytes(gal.n_rows, gal.padded_dim, nq)
+        ws = torch.empty(int(ws_bytes) + 256, dtype=torch.uint8, device=dev)
+        _cabi.check(lib.mmrs_search_topk_exhaustive(
+            g_ptr, gal.n_rows, gal.padded_dim, g_ld, g_dtype, qd.data_ptr(), nq, qd.stride(0), k,
+            int(bool(normalize_queries)), float(scale), gal.row_offset, dv.data_ptr(), di.data_ptr(),
+            DeviceGallery.aligned_ptr(ws), ws_bytes, _stream_handle(dev)))
+        if dv is not values:
+            values.copy_(dv)
+            indices.copy_(di)
+        del ws
+
+
 def search_topk(queries, gallery: GalleryLike, k: int, *, normalize_queries: bool = True,
-                scale: float = 1.0, mode: Optional[str] = None, path: str = "auto", sync: bool = True):
+                scale: float = 1.0, mode: Optional[str] = None, path: str = "auto", sync: bool = True,
+                out=None):
     """Per-query top-k of `scale * q @ G.T` without materialising the score matrix.
 
     Returns `(values [Q, k] fp32 descending, indices [Q, k] int64)` exactly like
@@ -105,7 +129,9 @@ def search_topk(queries, gallery: GalleryLike, k: int, *, normalize_queries: boo
     Host queries (CPU tensor / numpy) give host results -- the reference's call shape
     (host in, `.cpu()` out, code/search_image.py:105-109) -- device queries give device results.
     `sync=False` enqueues the search on the current stream and returns a PendingSearch, so several
-    batches can be in flight.
+    batches can be in flight.  `out=(values, indices)` writes into caller-owned tensors (pinned host
+    tensors for host queries) instead of allocating; either way the library replays ONE captured
+    graph per (shape, stream) slot and only re-points its query / result nodes.
     """
     gal = _as_gallery(gallery, mode)
     q, on_host = _prep_queries(queries, gal)
@@ -120,33 +146,48 @@ def search_topk(queries, gallery: GalleryLike, k: int, *, normalize_queries: boo
     if torch.cuda.current_device() != dev.index:
         torch.cuda.set_device(dev)
     stream = torch.cuda.current_stream(dev)
-    ws_ptr, ws_bytes = gal.search_workspace(nq, k, on_host, stream.cuda_stream)
-    if on_host:
-        if nq > 0 and not q.is_pinned():
-            q = q.pin_memory()
+    if out is not None:
+        values, indices = out
+        if (tuple(values.shape) != (nq, k) or tuple(indices.shape) != (nq, k) or values.dtype != torch.float32
+                or indices.dtype != torch.int64 or values.is_cuda == on_host or indices.is_cuda == on_host
+                or not values.is_contiguous() or not indices.is_contiguous()):
+            raise ValueError(f"out must be contiguous (float32 [{nq}, {k}], int64 [{nq}, {k}]) tensors on the "
+                             f"{'host' if on_host else 'device'}")
+    elif on_host:
         values = torch.empty((nq, k), dtype=torch.float32, pin_memory=True)
         indices = torch.empty((nq, k), dtype=torch.int64, pin_memory=True)
     else:
         values = torch.empty((nq, k), dtype=torch.float32, device=dev)
         indices = torch.empty((nq, k), dtype=torch.int64, device=dev)
     if nq == 0:
-        return (values, indices) if sync else PendingSearch(values, indices, None, None, None)
+        return (values, indices) if sync else PendingSearch(values, indices, None, None, None, None, None)
+    if on_host and not q.is_pinned():
+        q = q.pin_memory()
+    slot = gal.search_slot(nq, k, on_host, stream.cuda_stream)
     g_ptr, g_ld, g_dtype = _operand(gal, nq, path)
     args = (g_ptr, gal.n_rows, gal.padded_dim, g_ld, g_dtype,
             q.data_ptr(), nq, q.stride(0), k, int(bool(normalize_queries)), float(scale),
-            gal.row_offset, _cabi.PATHS[path], values.data_ptr(), indices.data_ptr(), ws_ptr, ws_bytes)
+            gal.row_offset, _cabi.PATHS[path], values.data_ptr(), indices.data_ptr(), slot.ptr, slot.nbytes)
+
+    def redo(v, i):
+        _search_exhaustive(gal, q, k, normalize_queries, scale, path, v, i)
+
     if sync:
         fn = lib.mmrs_search_topk_host if on_host else lib.mmrs_search_topk
-        _cabi.check(fn(*args, stream.cuda_stream))
+        st = fn(*args, stream.cuda_stream)
+        if st == _cabi.ERR_RETRY:
+            redo(values, indices)
+        else:
+            _cabi.check(st)
         return values, indices
-    status = torch.zeros(1, dtype=torch.int32).pin_memory()
+    ticket, status, event = slot.acquire()
     fn = lib.mmrs_search_topk_host_async if on_host else lib.mmrs_search_topk_async
-    _cabi.check(fn(*args, status.data_ptr(), stream.cuda_stream))
-    event = torch.cuda.Event()
+    st = fn(*args, status.data_ptr(), stream.cuda_stream)
+    if st != _cabi.OK:
+        slot.release(ticket)
+        _cabi.check(st)
     event.record(stream)
-    pend = PendingSearch(values, indices, status, event,
-                         lambda: search_topk(queries, gal, k, normalize_queries=normalize_queries, scale=scale,
-                                             path=path, sync=True))
+    pend = PendingSearch(values, indices, slot, ticket, status, event, redo)
     pend._keepalive = q        # the enqueued copies / kernels read it
     return pend
 
@@ -177,7 +218,11 @@ def full_scores(queries, gallery: GalleryLike, *, normalize_queries: bool = True
 
 
 # one-entry upload cache: the reference re-uploads `features` on every call (:107); a script that
-# passes the same host tensor again (same storage, same version) reuses the resident copy
+# passes the SAME host tensor object again (identity, same in-place version) reuses the resident copy.
+# The entry holds a strong reference to that tensor, so its address cannot be recycled by a different
+# tensor while the entry lives (a data_ptr key could: the allocator reuses freed blocks at once).
+# numpy arrays have no version counter -- in-place edits are invisible -- and are uploaded every time;
+# pass a DeviceGallery to keep a gallery resident explicitly.
 _last_upload: dict = {}
 
 
@@ -185,14 +230,12 @@ def _resident(features, mode: Optional[str]) -> DeviceGallery:
     if isinstance(features, DeviceGallery):
         return features
     if isinstance(features, np.ndarray):
-        features = torch.from_numpy(features)
-    key = (features.data_ptr(), tuple(features.shape), features.dtype, features._version, mode)
-    hit = _last_upload.get("key")
-    if hit == key:
-        return _last_upload["gallery"]
+        return DeviceGallery(torch.from_numpy(features), mode=mode)
+    hit = _last_upload.get("entry")
+    if hit is not None and hit[0] is features and hit[1] == features._version and hit[2] == mode:
+        return hit[3]
     gal = DeviceGallery(features, mode=mode)
-    _last_upload["key"] = key
-    _last_upload["gallery"] = gal
+    _last_upload["entry"] = (features, features._version, mode, gal)
     return gal
 
 
@@ -262,31 +305,182 @@ def mix_image_text_query(image_prototype, text_embedding):
     return (torch.as_tensor(image_prototype) + torch.as_tensor(text_embedding)) / 2
 
 
+def image_text_prototypes(image_features, text_embedding):
+    """The arithmetic of `get_image_text_features` (code/search_image.py:128-140) on already encoded
+    sample features [S, D] (as they leave `encode_image`, not yet normalised) and the class's text
+    embedding [D]: returns `(image_features, image_text_features)` --
+      image_text_features = mean over samples of (unit image row + unit text row) / 2   (:135-136)
+      image_features      = mean of the unit image rows, re-normalised                    (:137-139)
+    S is the shot count (<= 50): host torch, like the reference's few-row tensors."""
+    img = torch.as_tensor(image_features).detach().to(torch.float32).clone()
+    txt = torch.as_tensor(text_embedding).detach().to(torch.float32).reshape(1, -1).repeat(img.shape[0], 1)
+    txt /= txt.norm(dim=-1, keepdim=True)
+    img /= img.norm(dim=-1, keepdim=True)
+    image_text_features = ((img + txt) / 2.).mean(dim=0)
+    image_mean = img.mean(dim=0)
+    image_mean /= image_mean.norm()
+    return image_mean, image_text_features
+
+
+def _encode_samples(clip_model, preprocess, sample_images, class_name):
+    """Load and encode the sample images exactly as the reference's query builders do
+    (code/search_image.py:120-131, :187-196): `dataset_path/class_name/sample`, RGB, `preprocess`,
+    stacked, `clip_model.encode_image`.  The encoder is the caller's (out of scope here)."""
+    from PIL import Image
+    images = []
+    class_path = os.path.join(dataset_path, class_name)
+    for sample_img in sample_images:
+        with open(os.path.join(class_path, sample_img), "rb") as f:
+            images.append(preprocess(Image.open(f).convert("RGB")))
+    images = torch.stack(images, dim=0)
+    try:
+        images = images.to(next(clip_model.parameters()).device)
+    except (AttributeError, StopIteration, TypeError):
+        pass
+    with torch.no_grad():
+        return clip_model.encode_image(images)
+
+
+def get_image_text_features(clip_model, preprocess, class_embeddings, sample_images, class_name):
+    """Drop-in for code/search_image.py:119-140 -> (image_features [D], image_text_features [D])."""
+    feats = _encode_samples(clip_model, preprocess, sample_images, class_name)
+    return image_text_prototypes(feats.float().cpu(), torch.as_tensor(class_embeddings[class_to_idx[class_name]]).cpu())
+
+
+def cluster_prototype(image_features, shots: int, *, random_state=None):
+    """The arithmetic of `get_cluster_features` (code/search_image.py:197-232) on encoded sample
+    features: unit-normalise, 2-means, then the mean of the `shots` samples nearest to the global
+    centre (clusters of similar size, :210-213) or to the majority cluster's centre (:214-227).
+    `random_state` seeds KMeans (the reference leaves it unseeded).  Returns a [D] fp32 tensor."""
+    from collections import Counter
+    from sklearn.cluster import KMeans
+    f = torch.as_tensor(image_features).detach().to(torch.float32)
+    f = (f / f.norm(dim=-1, keepdim=True)).cpu().numpy()
+    kmeans = KMeans(n_clusters=2, random_state=random_state)
+    kmeans.fit(f)
+    cluster_labels = kmeans.labels_
+    label_counts = Counter(cluster_labels)
+    majority_label = max(label_counts, key=label_counts.get)
+    if abs(label_counts[0] - label_counts[1]) / len(cluster_labels) < 0.2:
+        distances = np.linalg.norm(f - kmeans.cluster_centers_.mean(axis=0), axis=1)
+        nearest_indices = np.argsort(distances)[:shots]
+    else:
+        majority_mask = (cluster_labels == majority_label)
+        distances = np.linalg.norm(f[majority_mask] - kmeans.cluster_centers_[majority_label], axis=1)
+        nearest_indices = np.where(majority_mask)[0][np.argsort(distances)[:shots]]
+    return torch.tensor(np.mean(f[nearest_indices], axis=0))
+
+
+def get_cluster_features(clip_model, preprocess, sample_imgs, shots, class_name):
+    """Drop-in for code/search_image.py:185-232 (host result; the reference moves it to the GPU)."""
+    return cluster_prototype(_encode_samples(clip_model, preprocess, sample_imgs, class_name).float().cpu(), shots)
+
+
+# ---- top-k over an existing score matrix; cls_acc (code/utils.py:15-39) --------------------------------
+def topk_of_scores(scores, k: int):
+    """`scores.topk(k, 1, True, True)` (code/utils.py:17) for a [N, C] score matrix that already
+    exists (the Tip-Adapter logits of code/main_custom.py): one select CTA per row on packed
+    (score, ~column) keys -- values descending, equal scores by ascending column.  C * 1 lists of
+    length C: C may be anything, k <= min(C, 1024).  Host input gives a host result."""
+    t = scores if isinstance(scores, torch.Tensor) else torch.as_tensor(np.asarray(scores))
+    if t.dim() != 2:
+        raise ValueError("scores must be [N, C]")
+    n, c = int(t.shape[0]), int(t.shape[1])
+    k = int(k)
+    if k < 1:
+        raise ValueError("k must be >= 1")
+    if k > c:
+        raise RuntimeError("selected index k out of range")
+    on_host = not t.is_cuda
+    dev = t.device if t.is_cuda else torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0)
+    _cabi.require_b200(dev.index or 0)
+    lib = _cabi.lib
+    with torch.cuda.device(dev):
+        v_in = t.detach().to(device=dev, dtype=torch.float32).contiguous()
+        i_in = torch.arange(c, dtype=torch.int64, device=dev).repeat(n, 1)
+        out_v = torch.empty((n, k), dtype=torch.float32, device=dev)
+        out_i = torch.empty((n, k), dtype=torch.int64, device=dev)
+        if n:
+            ws_bytes = lib.mmrs_topk_merge_workspace_bytes(1, n, c)
+            ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=dev)
+            _cabi.check(lib.mmrs_topk_merge(v_in.data_ptr(), i_in.data_ptr(), 1, n, c, k, out_v.data_ptr(),
+                                            out_i.data_ptr(), DeviceGallery.aligned_ptr(ws), ws_bytes,
+                                            _stream_handle(dev)))
+    return (out_v.cpu(), out_i.cpu()) if on_host else (out_v, out_i)
+
+
+def cls_acc(output, target, topk=1, exclude_class=None):
+    """Drop-in for code/utils.py:15-39: percentage of rows whose `topk` best-scoring classes contain
+    the target; rows with `target == exclude_class` are left out; 0.0 when nothing is left.  The
+    top-k (:17) runs on the GPU select kernel (`topk_of_scores`)."""
+    target = torch.as_tensor(target)
+    pred = topk_of_scores(output, topk)[1].t().to(target.device)          # [topk, batch]
+    correct = pred.eq(target.view(1, -1).expand_as(pred))
+    mask = target.ne(exclude_class) if exclude_class is not None else torch.ones_like(target, dtype=torch.bool)
+    correct = correct[:, mask]
+    valid_num = mask.sum().item()
+    if valid_num == 0:
+        return 0.0
+    acc = correct.any(dim=0).float().sum().item()
+    return 100 * acc / valid_num
+
+
+# ---- logit_scale * F.cosine_similarity (code/merge_dataset.py:275-278, :303) ------------------------------
+def cosine_similarity_scores(image_features, text_features, logit_scale=1.0, eps: float = 1e-8):
+    """`logit_scale * torch.nn.functional.cosine_similarity(image_features, text_features)` for image rows
+    [B, D] against ONE text row ([1, D] or [D], the reference's use): each side is divided by
+    max(||x||, eps) -- torch's clamp semantics, NOT the `x / x.norm()` idiom of search_image.py:157 (a zero
+    row scores 0 here, NaN there) -- then the rows are scored by the gallery scan with scale = logit_scale.
+    Returns [B] fp32 (host input -> host result)."""
+    x = image_features if isinstance(image_features, torch.Tensor) else torch.as_tensor(np.asarray(image_features))
+    t = text_features if isinstance(text_features, torch.Tensor) else torch.as_tensor(np.asarray(text_features))
+    t = t.detach().to(torch.float32).reshape(-1, x.shape[-1])
+    if x.dim() != 2 or t.shape[0] != 1:
+        raise ValueError("image_features must be [B, D] and text_features one row ([1, D] or [D])")
+    on_host = not x.is_cuda
+    x = x.detach().to(torch.float32)
+    xn = x / x.norm(dim=1, keepdim=True).clamp_min(eps)
+    tn = (t / t.norm(dim=1, keepdim=True).clamp_min(eps)).to(x.device)
+    scale = float(logit_scale.detach().float().item()) if isinstance(logit_scale, torch.Tensor) else float(logit_scale)
+    out = full_scores(tn, DeviceGallery(xn, mode="fp32"), normalize_queries=False, scale=scale)[0]
+    return out.cpu() if on_host else out
+
+
 # ---- threshold sweep (SURVEY.md section 8 row f2) ---------------------------------------------------
+def _is_f64(x) -> bool:
+    if isinstance(x, torch.Tensor):
+        return x.dtype == torch.float64
+    a = np.asarray(x)
+    return a.dtype == np.float64 or a.dtype.kind not in "f"      # python floats / ints compare as float64 in numpy
+
+
 def threshold_sweep_counts(pos_res, neg_res, thresholds, device: Optional[torch.device] = None):
     """(tp [T], fp [T]) int64 numpy: tp[t] = #{pos >= thresholds[t]}, fp likewise, on the GPU.
-    Thresholds must be ascending (np.linspace(min, max, T) is)."""
+    Thresholds must be ascending (np.linspace(min, max, T) is).  The comparison is numpy's: float32
+    scores are promoted to float64 against the float64 grid; float64 scores (e.g. Python floats, a
+    float64 similarity matrix) are compared as they are -- they are never rounded to float32."""
     thr = np.ascontiguousarray(np.asarray(thresholds, dtype=np.float64).reshape(-1))
     if thr.size > 1 and np.any(np.diff(thr) < 0):
         raise ValueError("thresholds must be ascending")
     dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0)
     _cabi.require_b200(dev.index or 0)
+    f64 = _is_f64(pos_res) or _is_f64(neg_res)
+    tdt, ndt = (torch.float64, np.float64) if f64 else (torch.float32, np.float32)
 
-    def dev_f32(x):
+    def dev_scores(x):
         if isinstance(x, torch.Tensor):
-            return x.detach().to(device=dev, dtype=torch.float32).contiguous().reshape(-1)
-        return torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float32).reshape(-1))).to(dev)
+            return x.detach().to(device=dev, dtype=tdt).contiguous().reshape(-1)
+        return torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=ndt).reshape(-1))).to(dev)
 
     with torch.cuda.device(dev):
-        p, n = dev_f32(pos_res), dev_f32(neg_res)
+        p, n = dev_scores(pos_res), dev_scores(neg_res)
         t = torch.from_numpy(thr).to(dev)
         out = torch.empty((thr.size, 2), dtype=torch.int64, device=dev)
         ws_bytes = _cabi.lib.mmrs_threshold_sweep_workspace_bytes(thr.size)
         ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=dev)
-        _cabi.check(_cabi.lib.mmrs_threshold_sweep(p.data_ptr(), p.numel(), n.data_ptr(), n.numel(),
-                                                   t.data_ptr(), thr.size, out.data_ptr(),
-                                                   DeviceGallery.aligned_ptr(ws), ws_bytes,
-                                                   _stream_handle(dev)))
+        fn = _cabi.lib.mmrs_threshold_sweep_f64 if f64 else _cabi.lib.mmrs_threshold_sweep
+        _cabi.check(fn(p.data_ptr(), p.numel(), n.data_ptr(), n.numel(), t.data_ptr(), thr.size, out.data_ptr(),
+                       DeviceGallery.aligned_ptr(ws), ws_bytes, _stream_handle(dev)))
         counts = out.cpu().numpy()
     return counts[:, 0].copy(), counts[:, 1].copy()
 
@@ -346,7 +540,7 @@ def evaluate_thresholds(similarities, thresholds, positive_class, negative_class
     sim64 = np.array([it["similarity"] for it in rel], dtype=np.float64)
     sim32 = sim64.astype(np.float32)
     if not np.array_equal(sim32.astype(np.float64), sim64):
-        raise ValueError("similarities must be fp32-representable (they are float(fp32 cosine) in the lab scripts)")
+        sim32 = sim64      # not float32-representable: compared in float64, exactly as the reference's Python floats
     is_pos = np.array([it["true_label"] == positive_class for it in rel], dtype=bool)
     total_pos, total_neg = int(is_pos.sum()), int((~is_pos).sum())
     thr = np.asarray(thresholds, dtype=np.float64).reshape(-1)

@@ -14,6 +14,7 @@ from __future__ import annotations
 import math
 from typing import Callable, Optional
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -94,6 +95,7 @@ class ShardedGallery:
     `local` is the rank's DeviceGallery with `row_offset` = first global row.  `local_search` and
     `merge` exist so the host-side protocol (gather layout, index offsets, tie rule) can be
     exercised on CPU with the gloo backend in tests; the product defaults are the CUDA kernels.
+    `fused=False` forces the NCCL all-gather variant (also: MMRS_NO_FUSED_GATHER=1).
     """
 
     def __init__(self, local, n_rows_global: int, group: Optional[dist.ProcessGroup] = None,
@@ -108,98 +110,153 @@ class ShardedGallery:
         self._fused = {}
         import os
         self._fused_ok = os.environ.get("MMRS_NO_FUSED_GATHER", "0") != "1" if fused is None else bool(fused)
+        self._fused_used = False
         if local_search is None:
             from .search import search_topk as local_search
         self._search = local_search
         self._merge = merge or _merge_cuda
+        # the shortest shard decides how many keys every rank contributes per query: ONE k_local for all
+        # ranks (buffer strides and the merge shape must agree); shards shorter than k use the padded
+        # NCCL variant.  One small collective at construction.
+        self.min_shard_rows = len(local)
+        if self.world > 1:
+            sizes = [None] * self.world
+            dist.all_gather_object(sizes, len(local), group=group)
+            self.min_shard_rows = int(min(sizes))
 
     @property
     def fused_active(self) -> bool:
         """True once a search of this handle has gone through the fused NVLink gather."""
-        return bool(self._fused) and self._fused_ok
+        return self._fused_used and self._fused_ok
 
     @classmethod
     def from_full(cls, features: torch.Tensor, mode: Optional[str] = None, device=None,
-                  group: Optional[dist.ProcessGroup] = None) -> "ShardedGallery":
+                  group: Optional[dist.ProcessGroup] = None, **kw) -> "ShardedGallery":
         """Every rank is handed the full host matrix and keeps only its block."""
         world = dist.get_world_size(group) if dist.is_initialized() else 1
         rank = dist.get_rank(group) if dist.is_initialized() else 0
         lo, hi = shard_bounds(features.shape[0], world)[rank]
         local = DeviceGallery(features[lo:hi], mode=mode, device=device, row_offset=lo)
-        return cls(local, features.shape[0], group)
+        return cls(local, features.shape[0], group, **kw)
 
-    def _search_topk_keys(self, queries, k: int, normalize_queries: bool, scale: float, path: str):
-        """CUDA fast path: local top-k as packed 64-bit keys -> ONE all-gather (Q*k*8 bytes per rank)
-        -> merge kernel reading the gathered buffer in place.  Nothing synchronises with the host
-        until the final status check."""
+    # ---- per-slot buffers ---------------------------------------------------------------------------------
+    def _stage_queries(self, slot, queries):
+        """fp32 [Q, padded_dim] queries on the device, in a buffer the slot owns (so the library's graph
+        of this slot keeps its query pointer); host queries are copied asynchronously."""
         from .search import _prep_queries
         gal = self.local
         q, on_host = _prep_queries(queries, gal)
+        if not on_host:
+            return q, False, None
+        qd = slot.extra.get("q_dev")
+        if qd is None or qd.shape != q.shape:
+            qd = slot.extra["q_dev"] = torch.empty(q.shape, dtype=torch.float32, device=gal.device)
+        if not q.is_pinned():
+            q = q.pin_memory()
+        qd.copy_(q, non_blocking=True)
+        return qd, True, q
+
+    @staticmethod
+    def _results(slot, nq, k, dev, on_host, out):
+        """(device result tensors the kernels write, host tensors handed back or None)."""
         if on_host:
-            q = q.to(gal.device, non_blocking=True)
-        nq = int(q.shape[0])
+            dv = slot.extra.get("out_v")
+            if dv is None or dv.shape != (nq, k):
+                dv = slot.extra["out_v"] = torch.empty((nq, k), dtype=torch.float32, device=dev)
+                slot.extra["out_i"] = torch.empty((nq, k), dtype=torch.int64, device=dev)
+            di = slot.extra["out_i"]
+            if out is not None:
+                hv, hi = out
+            else:
+                hv = torch.empty((nq, k), dtype=torch.float32, pin_memory=True)
+                hi = torch.empty((nq, k), dtype=torch.int64, pin_memory=True)
+            return dv, di, hv, hi
+        if out is not None:
+            return out[0], out[1], None, None
+        return (torch.empty((nq, k), dtype=torch.float32, device=dev),
+                torch.empty((nq, k), dtype=torch.int64, device=dev), None, None)
+
+    def _search_topk_keys(self, queries, k: int, normalize_queries: bool, scale: float, path: str, out=None):
+        """CUDA fast path: local top-k as packed 64-bit keys -> ONE all-gather (Q*k*8 bytes per rank)
+        -> merge kernel reading the gathered buffer in place.  Nothing synchronises with the host
+        until the final status check.  Shards shorter than k pad their lists with key 0."""
+        gal = self.local
         dev = gal.device
         lib = _cabi.lib
         if torch.cuda.current_device() != dev.index:
             torch.cuda.set_device(dev)
-        k_local = min(k, gal.n_rows)
-        n_keys = nq * k
-        buf = torch.zeros(n_keys + 1, dtype=torch.int64, device=dev)      # key 0 = "no entry"; [-1] = status
-        status = torch.zeros(2, dtype=torch.int32).pin_memory()
         stream = torch.cuda.current_stream(dev)
-        ws_ptr, ws_bytes = gal.search_workspace(nq, k_local, False, stream.cuda_stream)
+        nq = int(queries.shape[0]) if hasattr(queries, "shape") and len(queries.shape) == 2 else 1
+        k_local = min(k, gal.n_rows)
+        slot = gal.search_slot(nq, k_local, False, stream.cuda_stream)
+        q, on_host, keep = self._stage_queries(slot, queries)
+        n_keys = nq * k
+        bufs = slot.extra.get(("keys", k))
+        if bufs is None:
+            bufs = slot.extra[("keys", k)] = (
+                torch.zeros(n_keys + 1, dtype=torch.int64, device=dev),                # key 0 = "no entry"; [-1] = status
+                torch.zeros(nq * k_local + 1, dtype=torch.int64, device=dev) if k_local != k else None,
+                torch.empty((self.world, n_keys + 1), dtype=torch.int64, device=dev),
+                torch.empty(1, dtype=torch.int32, device=dev))
+        buf, short, gathered, d_status = bufs
+        dv, di, hv, hi = self._results(slot, nq, k, dev, on_host, out)
+        ticket, status, event = slot.acquire()
+        shard_status = None
         if nq:
-            dst = buf if k_local == k else torch.empty(nq * k_local + 1, dtype=torch.int64, device=dev)
-            _cabi.check(lib.mmrs_search_topk_keys_async(
+            dst = buf if short is None else short
+            st = lib.mmrs_search_topk_keys_async(
                 gal.data.data_ptr(), gal.n_rows, gal.padded_dim, gal.data.stride(0), gal.dtype_code,
                 q.data_ptr(), nq, q.stride(0), k_local, int(bool(normalize_queries)), float(scale),
-                gal.row_offset, _cabi.PATHS[path], dst.data_ptr(), ws_ptr, ws_bytes, status.data_ptr(),
-                stream.cuda_stream))
-            if dst is not buf:                       # a shard shorter than k: pad its lists with key 0
-                buf[:n_keys].view(nq, k)[:, :k_local] = dst[:-1].view(nq, k_local)
-                buf[-1] = dst[-1]
-        gathered = _all_gather(buf, self.world, self.group)               # [world, nq*k + 1]
-        out_v = torch.empty((nq, k), dtype=torch.float32, device=dev)
-        out_i = torch.empty((nq, k), dtype=torch.int64, device=dev)
+                gal.row_offset, _cabi.PATHS[path], dst.data_ptr(), slot.ptr, slot.nbytes, status.data_ptr(),
+                stream.cuda_stream)
+            if st != _cabi.OK:
+                slot.release(ticket)
+                _cabi.check(st)
+            if short is not None:                       # a shard shorter than k: the rest of its lists stays key 0
+                buf[:n_keys].view(nq, k)[:, :k_local] = short[:-1].view(nq, k_local)
+                buf[-1] = short[-1]
+        dist.all_gather_into_tensor(gathered.view(-1), buf, group=self.group)      # [world, nq*k + 1]
         if nq:
-            d_status = torch.empty(1, dtype=torch.int32, device=dev)
             _cabi.check(lib.mmrs_topk_merge_keys_async(gathered.data_ptr(), self.world, nq, k, n_keys + 1, k,
-                                                       out_v.data_ptr(), out_i.data_ptr(), d_status.data_ptr(),
+                                                       dv.data_ptr(), di.data_ptr(), d_status.data_ptr(),
                                                        status[1:].data_ptr(), stream.cuda_stream))
-            shard_status = gathered[:, -1].to("cpu", non_blocking=True)
-        else:
-            shard_status = None
+            table = slot.extra.get("shard_status")          # one pinned row per status ticket of the slot
+            if table is None or table.shape[0] <= ticket:
+                table = slot.extra["shard_status"] = torch.zeros((max(ticket + 1, slot.N_STATUS), self.world),
+                                                                 dtype=torch.int64).pin_memory()
+            shard_status = table[ticket]
+            shard_status.copy_(gathered[:, -1], non_blocking=True)
         if on_host:
-            hv = torch.empty((nq, k), dtype=torch.float32, pin_memory=True)
-            hi = torch.empty((nq, k), dtype=torch.int64, pin_memory=True)
-            hv.copy_(out_v, non_blocking=True)
-            hi.copy_(out_i, non_blocking=True)
-            out_v, out_i = hv, hi
-        event = torch.cuda.Event()
+            hv.copy_(dv, non_blocking=True)
+            hi.copy_(di, non_blocking=True)
         event.record(stream)
 
         def finish():
             event.synchronize()
+            res = (hv, hi) if on_host else (dv, di)
             if shard_status is None:
-                return out_v, out_i
+                slot.release(ticket)
+                return res
             worst = int(shard_status.max().item())
+            merge_rc = lib.mmrs_search_status(status[1:].data_ptr())
+            if worst not in (0, 1):                  # e.g. a zero-norm query: same error as single-GPU
+                status[0] = worst
+            own_rc = lib.mmrs_search_status(status.data_ptr()) if worst not in (0, 1) else _cabi.OK
+            slot.release(ticket)
             if worst == 1:
                 return None                          # some rank overflowed: ALL ranks take the general path
-            if worst != 0:                           # e.g. a zero-norm query: same error as single-GPU
-                status[0] = worst
-                _cabi.check(lib.mmrs_search_status(status.data_ptr()))
-            _cabi.check(lib.mmrs_search_status(status[1:].data_ptr()))
-            return out_v, out_i
+            _cabi.check(own_rc)
+            _cabi.check(merge_rc)
+            return res
 
-        finish._keepalive = (q, buf, gathered)
+        finish._keepalive = (q, keep)
         return finish
 
     # ---- search fused with its all-gather over NVLink peer memory -----------------------------------
-    def _fused_state(self, nq: int, k_local: int, stream_id: int):
+    def _fused_state(self, slot, nq: int, k_local: int):
         """Symmetric (peer-mapped) gather buffer + flag array of one (shape, stream) slot; the
         rendezvous is collective and happens once per slot."""
-        key = (nq, k_local, stream_id)
-        st = self._fused.get(key)
+        st = slot.extra.get("fused")
         if st is None:
             import torch.distributed._symmetric_memory as symm_mem
             dev = self.local.device
@@ -211,85 +268,96 @@ class ShardedGallery:
             torch.cuda.synchronize(dev)
             dist.barrier(group=self.group)                   # everyone zeroed before anyone stores
             ptrs = [int(x) for x in hdl.buffer_ptrs]
-            st = {"t": t, "hdl": hdl, "stride": stride, "epoch": 0,
+            flag_off = self.world * stride * 8
+            st = {"t": t, "hdl": hdl, "stride": stride,
                   "bufs": torch.tensor(ptrs, dtype=torch.int64, device=dev),
-                  "flags": torch.tensor([x + self.world * stride * 8 for x in ptrs], dtype=torch.int64, device=dev)}
-            self._fused[key] = st
+                  "flags": torch.tensor([x + flag_off for x in ptrs], dtype=torch.int64, device=dev),
+                  "local_flags": t.data_ptr() + flag_off}
+            slot.extra["fused"] = st
         return st
 
-    def _search_topk_fused(self, queries, k: int, normalize_queries: bool, scale: float, path: str):
+    def _search_topk_fused(self, queries, k: int, normalize_queries: bool, scale: float, path: str, out=None):
         """Local scan -> last select stores its keys into EVERY rank's buffer over NVLink and raises
-        a ready flag -> merge select waits for all flags.  One library call, no NCCL, no host sync
-        until the final status check."""
-        from .search import _prep_queries
+        a ready flag -> a one-warp kernel waits for all flags -> merge select.  One library call, one
+        graph replay, no NCCL, no host sync until the final status check; every buffer the call
+        touches belongs to the (shape, stream) slot and was allocated once."""
         gal = self.local
-        q, on_host = _prep_queries(queries, gal)
-        if on_host:
-            q = q.to(gal.device, non_blocking=True)
-        nq = int(q.shape[0])
         dev = gal.device
         lib = _cabi.lib
         if torch.cuda.current_device() != dev.index:
             torch.cuda.set_device(dev)
-        k_local = min(k, gal.n_rows)
         stream = torch.cuda.current_stream(dev)
-        st = self._fused_state(nq, k_local, stream.cuda_stream)
-        st["epoch"] += 1
-        ws_ptr, ws_bytes = gal.search_workspace(nq, k_local, False, stream.cuda_stream)
-        out_v = torch.empty((nq, k), dtype=torch.float32, device=dev)
-        out_i = torch.empty((nq, k), dtype=torch.int64, device=dev)
-        status = torch.zeros(2 * self.world + 2, dtype=torch.int32).pin_memory()
-        _cabi.check(lib.mmrs_search_topk_fused_gather_async(
+        nq = int(queries.shape[0])
+        k_local = min(k, self.min_shard_rows)            # the same on every rank
+        slot = gal.search_slot(nq, k_local, False, stream.cuda_stream)
+        st = self._fused_state(slot, nq, k_local)         # collective on first use of the slot
+        q, on_host, keep = self._stage_queries(slot, queries)
+        dv, di, hv, hi = self._results(slot, nq, k, dev, on_host, out)
+        ticket, status, event = slot.acquire()
+        rc = lib.mmrs_search_topk_fused_gather_async(
             gal.data.data_ptr(), gal.n_rows, gal.padded_dim, gal.data.stride(0), gal.dtype_code,
             q.data_ptr(), nq, q.stride(0), k_local, k, int(bool(normalize_queries)), float(scale),
             gal.row_offset, _cabi.PATHS[path], st["bufs"].data_ptr(), st["flags"].data_ptr(),
-            st["t"].data_ptr(), self.rank, self.world, st["stride"], st["epoch"],
-            out_v.data_ptr(), out_i.data_ptr(), ws_ptr, ws_bytes, status.data_ptr(), stream.cuda_stream))
+            st["t"].data_ptr(), st["local_flags"], self.rank, self.world, st["stride"],
+            dv.data_ptr(), di.data_ptr(), slot.ptr, slot.nbytes, status.data_ptr(), stream.cuda_stream)
+        if rc != _cabi.OK:
+            slot.release(ticket)
+            _cabi.check(rc)
         if on_host:
-            hv = torch.empty((nq, k), dtype=torch.float32, pin_memory=True)
-            hi = torch.empty((nq, k), dtype=torch.int64, pin_memory=True)
-            hv.copy_(out_v, non_blocking=True)
-            hi.copy_(out_i, non_blocking=True)
-            out_v, out_i = hv, hi
-        event = torch.cuda.Event()
+            hv.copy_(dv, non_blocking=True)
+            hi.copy_(di, non_blocking=True)
         event.record(stream)
+        self._fused_used = True
 
         def finish():
             event.synchronize()
             rc = lib.mmrs_gather_status(status.data_ptr(), self.world)
+            slot.release(ticket)
             if rc == _cabi.ERR_RETRY:
                 return None                  # the same verdict on every rank: all take the general path
+            if rc == _cabi.ERR_TIMEOUT:
+                self._fused_ok = False       # a peer is dead or diverged: later calls use NCCL (its own abort handling)
             _cabi.check(rc)
-            return out_v, out_i
+            return (hv, hi) if on_host else (dv, di)
 
-        finish._keepalive = (q, status)
+        finish._keepalive = (q, keep)
         return finish
 
     def search_topk(self, queries: torch.Tensor, k: int, *, normalize_queries: bool = True,
-                    scale: float = 1.0, path: str = "auto", sync: bool = True):
+                    scale: float = 1.0, path: str = "auto", sync: bool = True, out=None):
         """Global top-k, identical on every rank.  `queries` must be the same on all ranks.
         `sync=False` returns an object whose `.wait()` yields `(values, indices)`, so that several
-        batches (and their all-gathers) can be in flight."""
+        batches (and their all-gathers) can be in flight.  `out=(values, indices)`: caller-owned result
+        tensors (pinned host tensors for host queries)."""
         if k > self.n_rows_global:
             raise RuntimeError("selected index k out of range")
         if self._fast and self.world > 1:
-            nq = int(queries.shape[0]) if hasattr(queries, "shape") and len(queries.shape) == 2 else 1
-            fused = self._fused_ok and 1 <= nq <= 1024
+            if isinstance(queries, np.ndarray):
+                queries = torch.from_numpy(queries)
+            if queries.dim() == 1:
+                queries = queries.unsqueeze(0)
+            nq = int(queries.shape[0])
+            if nq == 0:
+                out_t = self.search_topk_general(queries, k, normalize_queries=normalize_queries, scale=scale, path=path)
+                return out_t if sync else _PendingSharded(lambda: out_t, None)
+            # fused NVLink gather: every rank must be able to contribute k_local keys with world * k_local >= k
+            fused = (self._fused_ok and 1 <= nq <= 1024 and self.world * min(k, self.min_shard_rows) >= k)
+            finish = None
             if fused:
                 try:
-                    finish = self._search_topk_fused(queries, k, normalize_queries, scale, path)
+                    finish = self._search_topk_fused(queries, k, normalize_queries, scale, path, out)
                 except (ImportError, AttributeError, RuntimeError) as e:   # no symmetric memory here
                     if isinstance(e, _cabi.MmrsError):
                         raise
-                    self._fused_ok = fused = False
-            if not fused:
-                finish = self._search_topk_keys(queries, k, normalize_queries, scale, path)
+                    self._fused_ok = False
+            if finish is None:
+                finish = self._search_topk_keys(queries, k, normalize_queries, scale, path, out)
             general = lambda: self.search_topk_general(queries, k, normalize_queries=normalize_queries,
                                                        scale=scale, path=path)
             pend = _PendingSharded(finish, general)
             return pend.wait() if sync else pend
-        out = self.search_topk_general(queries, k, normalize_queries=normalize_queries, scale=scale, path=path)
-        return out if sync else _PendingSharded(lambda: out, None)
+        out_t = self.search_topk_general(queries, k, normalize_queries=normalize_queries, scale=scale, path=path)
+        return out_t if sync else _PendingSharded(lambda: out_t, None)
 
     def search_topk_general(self, queries: torch.Tensor, k: int, *, normalize_queries: bool = True,
                             scale: float = 1.0, path: str = "auto"):

@@ -130,3 +130,80 @@ def overlap_grid_inputs() -> dict:
         "narrow": (np.array([0.50, 0.53], dtype=np.float32), np.array([0.48, 0.52], dtype=np.float32)),
         "separable": (np.array([30.0, 31.0, 35.0], dtype=np.float32), np.array([10.0, 12.0, 29.0], dtype=np.float32)),
     }
+
+
+# ---- query builders (code/search_image.py:119-140, :185-232, :295-318) ---------------------------------------
+QB_CLASSES = ["alpha", "beta", "gamma"]
+
+
+def query_builder_setup(root: str):
+    """A tiny on-disk dataset + stand-in encoder for the reference's query builders, which load sample
+    images from `dataset_path/class_name/`, `preprocess` them, stack and call `clip_model.encode_image`.
+    Returns (dataset_path, clip_model, preprocess, class_embeddings [3, 48], class_to_idx, samples) where
+    samples = {class: [file names]}; class "alpha" has two visual modes of very different sizes (14 + 6
+    images: k-means majority branch), class "beta" two balanced modes (10 + 10: global-mean branch)."""
+    from PIL import Image
+    rng = np.random.default_rng(9)
+    g = torch.Generator().manual_seed(9)
+    dataset_path = os.path.join(root, "data", "search")
+    samples = {}
+    modes = {"alpha": (14, 6), "beta": (10, 10), "gamma": (7, 0)}
+    for cls, (n_a, n_b) in modes.items():
+        os.makedirs(os.path.join(dataset_path, cls))
+        base_a = rng.integers(0, 256, size=(8, 8, 3))
+        base_b = rng.integers(0, 256, size=(8, 8, 3))
+        names = []
+        for i in range(n_a + n_b):
+            base = base_a if i < n_a else base_b
+            arr = np.clip(base + rng.integers(-12, 13, size=(8, 8, 3)), 0, 255).astype(np.uint8)
+            name = f"img_{i:02d}.png"
+            Image.fromarray(arr, "RGB").save(os.path.join(dataset_path, cls, name))
+            names.append(name)
+        samples[cls] = names
+    proj = torch.randn(192, 48, generator=g) / 14.0
+
+    def preprocess(img):
+        return torch.from_numpy(np.asarray(img, dtype=np.float32).copy()).permute(2, 0, 1) / 255.0 - 0.5
+
+    class Tower:
+        def encode_image(self, images):
+            return images.flatten(1) @ proj
+
+    class_embeddings = torch.randn(3, 48, generator=g) * 2.0          # NOT unit norm (:131 normalises)
+    class_to_idx = {c: i for i, c in enumerate(QB_CLASSES)}
+    return dataset_path, Tower(), preprocess, class_embeddings, class_to_idx, samples
+
+
+def cosine_inputs():
+    """(image_features [B, 512] un-normalised, text_features [1, 512], logit_scale) for
+    `logit_scale * F.cosine_similarity(image_features, text_features)` (code/merge_dataset.py:275-278)."""
+    g = torch.Generator().manual_seed(44)
+    x = torch.randn(300, 512, generator=g) * (0.2 + 3 * torch.rand(300, 1, generator=g))
+    t = torch.randn(1, 512, generator=g)
+    x[:40] += 1.5 * t
+    return x.contiguous(), t.contiguous(), torch.tensor(100.0)
+
+
+def greedy_inputs(root: str):
+    """Files of distinct sizes plus a symmetric 'similar' relation for the same-folder greedy loop
+    (tool/find_repeated_in_same_folder.py:56-106) run with stub hash functions: the hash of a file is its
+    id, two hashes compare similar iff the pair is in the relation.  Returns (folder, ids {path: id},
+    similar {frozenset({a, b})}, unreadable {id})."""
+    from PIL import Image
+    rng = np.random.default_rng(21)
+    folder = os.path.join(root, "same_folder")
+    os.makedirs(os.path.join(folder, "sub"))
+    n = 40
+    order = rng.permutation(n)
+    ids = {}
+    for rank, i in enumerate(order):                                 # distinct file sizes, unrelated to the id order
+        side = 4 + rank
+        arr = rng.integers(0, 256, size=(side, side, 3), dtype=np.uint8)
+        path = os.path.join(folder, "sub" if i % 5 == 0 else "", f"f{i:02d}.bmp")
+        Image.fromarray(arr, "RGB").save(path)
+        ids[path] = int(i)
+    similar = set()
+    for _ in range(45):
+        a, b = (int(v) for v in rng.choice(n, size=2, replace=False))
+        similar.add(frozenset((a, b)))
+    return folder, ids, similar, {3, 29}

@@ -16,6 +16,12 @@ their inputs' seeds and their OUTPUTS are stored (tests/golden/*.npz, *.json).
                          the seeded feature batches), calc_combined_metrics (:133-231)
   tool/find_repeated.py  calculate_image_hash (:6-19), get_all_images (:21-33),
                          find_and_remove_duplicate_images (:35-71)
+  code/search_image.py   get_image_text_features (:119-140), get_cluster_features (:185-232), outlier_filter
+                         (:295-318) on a tiny on-disk dataset with a stand-in encoder (a fixed projection)
+  code/merge_dataset.py  clip_en_predict (:259-284: logit_scale * F.cosine_similarity, thresholded)
+  tool/find_repeated_in_same_folder.py
+                         get_all_images (:24-36), find_and_remove_duplicate_images (:56-106) with stub
+                         hash functions (imagehash is absent): pins the greedy first-keeper walk
 
 The one patch applied: torch.Tensor.cuda is made a no-op (this container has no GPU and
 search_image.py:107 hard-codes `.cuda()`), so the reference's arithmetic runs as its torch CPU
@@ -35,8 +41,8 @@ import torch
 
 HERE = Path(__file__).resolve().parent
 sys.path.insert(0, str(HERE))
-from golden_inputs import (dedup_image_set, lab3_inputs, overlap_grid_inputs, similarity_inputs, topk_inputs,  # noqa: E402
-                           union_inputs)
+from golden_inputs import (cosine_inputs, dedup_image_set, greedy_inputs, lab3_inputs, overlap_grid_inputs,  # noqa: E402
+                           query_builder_setup, similarity_inputs, topk_inputs, union_inputs)
 
 
 def extract_functions(path: Path, names: list[str], namespace: dict) -> dict:
@@ -159,6 +165,71 @@ def main(ref_root: str) -> None:
             "remaining_in_delete_folder": sorted(rel(p) for p in ns3["get_all_images"](del_dir)),
         }
     (HERE / "find_repeated_golden.json").write_text(json.dumps(golden, indent=1, sort_keys=True))
+
+    # ---- code/search_image.py query builders ------------------------------------------------------------
+    from collections import Counter
+    from sklearn.cluster import KMeans
+    with tempfile.TemporaryDirectory() as tmp:
+        dataset_path, tower, preprocess, class_embeddings, class_to_idx, samples = query_builder_setup(tmp)
+        ns7 = {"os": os, "np": np, "torch": torch, "Image": Image, "KMeans": KMeans, "Counter": Counter,
+               "dataset_path": dataset_path, "class_to_idx": class_to_idx}
+        extract_functions(ref / "code" / "search_image.py",
+                          ["get_image_text_features", "get_cluster_features", "outlier_filter"], ns7)
+        out7 = {}
+        for cls in samples:
+            with torch.no_grad():
+                img_f, img_txt_f = ns7["get_image_text_features"](tower, preprocess, class_embeddings.clone(),
+                                                                  samples[cls], cls)
+            out7[f"{cls}_image_features"] = img_f.numpy()
+            out7[f"{cls}_image_text_features"] = img_txt_f.numpy()
+            out7[f"{cls}_outlier_filter"] = ns7["outlier_filter"](tower, preprocess, samples[cls], cls).numpy()
+        for cls, shots in (("alpha", 5), ("beta", 8)):
+            np.random.seed(0)                                   # the reference's KMeans is unseeded (:199)
+            with contextlib.redirect_stdout(io.StringIO()):     # it prints the cluster sizes (:208)
+                out7[f"{cls}_cluster_features"] = ns7["get_cluster_features"](tower, preprocess, samples[cls], shots, cls).numpy()
+        np.savez(HERE / "query_builders_golden.npz", **out7)
+
+    # ---- code/merge_dataset.py: logit_scale * F.cosine_similarity (:275-278) ------------------------------
+    ns8 = {"torch": torch, "device": "cpu"}
+    extract_functions(ref / "code" / "merge_dataset.py", ["clip_en_predict"], ns8)
+    x, t, logit_scale = cosine_inputs()
+
+    class CosModel:
+        def __init__(self):
+            self.logit_scale = torch.log(logit_scale)
+        def eval(self):
+            return self
+        def encode_image(self, images):
+            return images.clone()               # the function normalises in place (:270)
+        def encode_text(self, text_inputs):
+            return text_inputs.clone()
+
+    labels = torch.zeros(x.shape[0], dtype=torch.int64)
+    loader = [(x[lo:lo + 64], labels[lo:lo + 64]) for lo in range(0, x.shape[0], 64)]
+    out8 = {}
+    with np.errstate(all="ignore"):
+        for thr in (-3.0, 0.0, 2.5, 70.0):
+            preds, _ = ns8["clip_en_predict"](CosModel(), loader, t, thr)
+            out8[f"preds_{thr:g}"] = np.array([int(p) for p in preds], dtype=np.int64)
+    # the similarity the function thresholds (its lines :269-278 on the same inputs)
+    xi = x / x.norm(dim=-1, keepdim=True)
+    ti = t / t.norm(dim=-1, keepdim=True)
+    out8["similarity"] = (CosModel().logit_scale.exp() * torch.nn.functional.cosine_similarity(xi, ti)).numpy()
+    np.savez(HERE / "merge_dataset_golden.npz", **out8)
+
+    # ---- tool/find_repeated_in_same_folder.py: the greedy first-keeper loop (:56-106) ----------------------
+    with tempfile.TemporaryDirectory() as tmp:
+        folder, ids, similar, unreadable = greedy_inputs(tmp)
+        ns9 = {"os": os}
+        extract_functions(ref / "tool" / "find_repeated_in_same_folder.py",
+                          ["get_all_images", "find_and_remove_duplicate_images"], ns9)
+        ns9["calculate_perceptual_hash"] = lambda p, hash_size=8: None if ids[p] in unreadable else (ids[p],)
+        ns9["compare_hashes"] = lambda h1, h2, threshold=5: frozenset((h1[0], h2[0])) in similar
+        with contextlib.redirect_stdout(io.StringIO()):
+            deleted, refs, total = ns9["find_and_remove_duplicate_images"](folder, 5)
+        golden9 = {"deleted": [[ids[a], ids[b]] for a, b in deleted], "representatives": [ids[p] for p in refs],
+                   "total": total, "remaining": sorted(ids[p] for p in ns9["get_all_images"](folder))}
+    (HERE / "same_folder_golden.json").write_text(json.dumps(golden9, indent=1, sort_keys=True))
     print("golden vectors written to", HERE)
 
 

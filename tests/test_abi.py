@@ -35,7 +35,7 @@ def test_python_binding_covers_the_header(mm):
 
 def test_version_and_pure_host_queries(mm):
     lib = mm._cabi.lib
-    assert lib.mmrs_abi_version() == 1
+    assert lib.mmrs_abi_version() == mm._cabi.ABI_VERSION == 2
     # workspace queries are pure host arithmetic: usable without a device
     small = lib.mmrs_search_workspace_bytes(10_000, 512, 0, 100, 10)
     big = lib.mmrs_search_workspace_bytes(1_000_000, 512, 1, 256, 100)

@@ -43,7 +43,7 @@ def test_same_folder_wrapper(mm, oracle, tmp_path):
     folder = str(tmp_path)
     paths = mm.get_all_images(folder)
     before = set(paths)
-    deleted, refs, total = mm.find_and_remove_duplicate_images(folder, 0.9999)
+    deleted, refs, total = mm.find_and_remove_duplicate_images(folder, cosine_threshold=0.9999)
     assert total == len(paths)
     # oracle: same embedding, oracle pairs, oracle greedy walk in file-size order
     from mmrs_b200.dedup import pixel_embedding
@@ -68,21 +68,99 @@ def test_same_folder_wrapper(mm, oracle, tmp_path):
 
 
 def test_cross_folder_wrapper_matches_reference_golden(mm, tmp_path):
-    """With the pixel embedder the cosine predicate at 0.9999 reproduces the reference's MD5 join
-    on this image set, so the result tuple must equal the one recorded from find_repeated.py --
-    except which of two identical reference images is reported (hash dict: last wins; top-1: the
-    lower index wins) and unreadable files."""
+    """The GPU top-1 search finds the candidates, the reference's own predicate (equal MD5 of the RGB
+    bytes) confirms them: the result tuple equals the one recorded from find_repeated.py, including
+    WHICH of two identical reference images is reported (the last one, find_repeated.py:52)."""
     gold = json.loads((GOLDEN / "find_repeated_golden.json").read_text())
     ref_dir, del_dir = dedup_image_set(str(tmp_path))
     rel = lambda p: os.path.relpath(p, tmp_path)
     deleted, kept, n_ref, n_del = mm.find_and_remove_duplicate_images(ref_dir, del_dir)
     assert (n_ref, n_del) == (gold["n_ref"], gold["n_del"])
-    assert sorted(rel(a) for a, _ in deleted) == sorted(a for a, _ in gold["deleted"])
+    assert sorted([rel(a), rel(b)] for a, b in deleted) == gold["deleted"]
+    assert ["delete/nested/c_copy.png", "reference/sub/c_again.png"] in gold["deleted"]      # the last duplicate won
     assert sorted(rel(p) for p in kept) == gold["kept"]
-    for a, b in deleted:
-        want = dict(gold["deleted"])[rel(a)]
-        assert rel(b) == want or {rel(b), want} == {"reference/sub/c.png", "reference/sub/c_again.png"}
     assert sorted(rel(p) for p in mm.get_all_images(del_dir)) == gold["remaining_in_delete_folder"]
+
+
+def _save(arr, path):
+    from PIL import Image
+    Image.fromarray(arr, "RGB").save(path)
+
+
+def test_cross_folder_default_deletes_only_pixel_identical_files(mm, tmp_path):
+    """The default embedder is not injective (16 x 16 box resize, mean removed, unit norm): a brighter
+    copy, a flat-colour image and an upscaled copy all score cos = 1 against a reference image.  The
+    exact confirmation must keep them; only the pixel-identical file goes."""
+    rng = np.random.default_rng(5)
+    ref, dele = tmp_path / "ref", tmp_path / "del"
+    ref.mkdir(); dele.mkdir()
+    base = rng.integers(40, 160, size=(32, 32, 3), dtype=np.uint8)
+    flat = np.full((32, 32, 3), 90, dtype=np.uint8)
+    _save(base, ref / "base.png")
+    _save(flat, ref / "flat.png")
+    _save(base, dele / "identical.bmp")
+    _save((base.astype(np.int32) + 40).astype(np.uint8), dele / "brighter.png")
+    _save(np.full((32, 32, 3), 200, dtype=np.uint8), dele / "other_flat.png")
+    _save(np.kron(base, np.ones((2, 2, 1), dtype=np.uint8)), dele / "upscaled.png")
+    from mmrs_b200.dedup import pixel_embedding
+    emb_r, _ = pixel_embedding([str(ref / "base.png")])
+    emb_d, _ = pixel_embedding([str(dele / "brighter.png"), str(dele / "upscaled.png")])
+    assert float((emb_d @ emb_r.T).min()) > 0.9999             # the embedding alone would delete them
+    deleted, kept, n_ref, n_del = mm.find_and_remove_duplicate_images(str(ref), str(dele))
+    assert [os.path.basename(a) for a, _ in deleted] == ["identical.bmp"]
+    assert sorted(os.path.basename(p) for p in kept) == ["brighter.png", "other_flat.png", "upscaled.png"]
+    assert sorted(os.listdir(dele)) == ["brighter.png", "other_flat.png", "upscaled.png"]
+    # an explicit embedding predicate (confirm="none") is the caller's decision
+    deleted, kept, _, _ = mm.find_and_remove_duplicate_images(str(ref), str(dele), confirm="none", dry_run=True)
+    assert len(deleted) == 3 and kept == []
+
+
+@pytest.mark.parametrize("radius", [0, 5, 10, 1.5, 0.0])
+def test_hamming_radius_is_refused_not_reinterpreted(mm, tmp_path, radius):
+    """The reference's same-folder form takes a Hamming radius (0 = strictest, its main passes 5).  Neither
+    value may be read as a cosine: 5 would never match, 0 would delete nearly the whole folder."""
+    dedup_image_set(str(tmp_path))
+    before = sorted(mm.get_all_images(str(tmp_path)))
+    with pytest.raises(ValueError, match="Hamming radius"):
+        mm.find_and_remove_duplicate_images(str(tmp_path), radius)
+    with pytest.raises(ValueError, match="Hamming radius"):
+        mm.find_and_remove_duplicate_images(str(tmp_path), cosine_threshold=radius)
+    with pytest.raises(ValueError, match="Hamming radius"):
+        mm.find_and_remove_near_duplicate_images(str(tmp_path), radius)
+    assert sorted(mm.get_all_images(str(tmp_path))) == before      # nothing was deleted
+
+
+def test_non_unit_rows_keep_the_exact_pair_set(mm, oracle):
+    """The bf16 prefilter's margin bounds the rounding of UNIT rows; it is scaled by the largest squared
+    row norm, so raw (non-normalised) embeddings give the exact mode's pair set on the tensor-core path."""
+    gen = torch.Generator().manual_seed(11)
+    n, d = 4096, 128
+    x = oracle.l2_normalize(torch.randn(n, d, generator=gen)) * 3.0           # every row has norm 3
+    tau = 0.95 * 9.0
+    for t, c in enumerate(torch.linspace(0.940, 0.960, 200).tolist()):
+        a = x[t] / 3.0
+        r = torch.randn(d, generator=gen)
+        r = oracle.l2_normalize(r - (r @ a) * a)
+        x[2000 + t] = 3.0 * (c * a + (1 - c * c) ** 0.5 * r)
+    want = mm.find_duplicate_pairs(x, tau, method="fp32")
+    got = mm.find_duplicate_pairs(x, tau, method="tc")
+    assert torch.equal(got, want) and 60 < got.shape[0] < 140
+    assert torch.equal(mm.find_duplicate_pairs(x, tau), want)                 # "auto" takes the tensor-core path here
+    from mmrs_b200.dedup import row_norm_range, _device_f32
+    lo, hi = row_norm_range(_device_f32(x))
+    assert abs(lo - 3.0) < 1e-4 and abs(hi - 3.0) < 1e-4
+
+
+def test_library_pair_sort(mm):
+    """mmrs_sort_pairs (bitonic, packed keys) against numpy's lexsort, sizes around the tile boundaries."""
+    from mmrs_b200.dedup import sort_pairs
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 3, 1000, 2047, 2048, 2049, 4096, 5000, 70_001, 300_000):
+        a = rng.integers(0, 1 << 31, size=(n, 2), dtype=np.int64)
+        a[: n // 3, 0] = 7                                         # many equal first components
+        got = sort_pairs(torch.from_numpy(a).cuda(), 1 << 31).cpu().numpy()
+        want = a[np.lexsort((a[:, 1], a[:, 0]))]
+        np.testing.assert_array_equal(got, want)
 
 
 # ---- tensor-core prefilter + exact recheck -----------------------------------------------------------

@@ -229,3 +229,127 @@ def test_get_similarity_from_matrix_matches_reference(mm):
     np.testing.assert_array_equal(neg, g["sliced_neg"])
     pos2, neg2 = mm.get_similarity_from_matrix(sim.numpy(), targets, label)
     np.testing.assert_array_equal(pos2, pos) and np.testing.assert_array_equal(neg2, neg)
+
+
+# ---- pinned against outputs of the reference's own function bodies (tests/golden/make_golden.py) ----------------
+def _greedy_case(tmp_path):
+    """The same-folder greedy loop's inputs as (n, pairs, order by file size desc, unreadable ids, golden)."""
+    import json
+    from conftest import GOLDEN
+    from golden_inputs import greedy_inputs
+    gold = json.loads((GOLDEN / "same_folder_golden.json").read_text())
+    folder, ids, similar, unreadable = greedy_inputs(str(tmp_path))
+    paths = sorted(ids, key=lambda p: os.path.getsize(p), reverse=True)      # find_repeated_in_same_folder.py:73
+    order = [ids[p] for p in paths if ids[p] not in unreadable]                # hash None -> skipped (:78)
+    pairs = sorted(tuple(sorted(s)) for s in similar)
+    return len(ids), pairs, order, gold
+
+
+def test_greedy_walk_matches_reference_same_folder_loop(mm, oracle, tmp_path):
+    """greedy_first_keeper (product) and greedy_keep_first (oracle) against the result tuple recorded from
+    tool/find_repeated_in_same_folder.py:56-106 run with stub hash functions."""
+    n, pairs, order, gold = _greedy_case(tmp_path)
+    for fn in (lambda: mm.greedy_first_keeper(n, np.array(pairs), order), lambda: oracle.greedy_keep_first(n, pairs, order)):
+        reps, dups = fn()
+        assert reps == gold["representatives"]
+        assert [list(d) for d in dups] == gold["deleted"]
+    assert gold["total"] == n
+
+
+def test_same_folder_wrapper_matches_reference_loop(mm, tmp_path, monkeypatch):
+    """The whole same-folder wrapper (listing, size sort, skip of unreadable files, greedy walk, deletion,
+    result tuple) against the recorded reference run: the pair predicate is injected where the CUDA
+    self-join sits, everything else is the product code."""
+    import mmrs_b200.dedup as D
+    from golden_inputs import greedy_inputs
+    import json
+    from conftest import GOLDEN
+    gold = json.loads((GOLDEN / "same_folder_golden.json").read_text())
+    folder, ids, similar, unreadable = greedy_inputs(str(tmp_path))
+
+    def embed(paths):                                   # "embedding" = the id; unreadable files flagged
+        ok = np.array([ids[p] not in unreadable for p in paths])
+        return torch.tensor([[float(ids[p])] for p, good in zip(paths, ok) if good]), ok
+
+    def fake_pairs(emb, threshold, **kw):               # stands in for the GPU self-join
+        idv = [int(v) for v in emb[:, 0].tolist()]
+        out = [(i, j) for i in range(len(idv)) for j in range(i + 1, len(idv)) if frozenset((idv[i], idv[j])) in similar]
+        return torch.tensor(out, dtype=torch.int64).reshape(-1, 2)
+
+    monkeypatch.setattr(D, "find_duplicate_pairs", fake_pairs)
+    deleted, refs, total = D.find_and_remove_duplicate_images(folder, cosine_threshold=0.95, embed=embed)
+    assert [[ids[a], ids[b]] for a, b in deleted] == gold["deleted"]
+    assert [ids[p] for p in refs] == gold["representatives"] and total == gold["total"]
+    assert sorted(ids[p] for p in D.get_all_images(folder)) == gold["remaining"]
+
+
+def test_query_builders_match_reference(mm, oracle, tmp_path, monkeypatch):
+    """get_image_text_features (:119-140), get_cluster_features (:185-232) and the outlier_filter arithmetic
+    (:310-318) against outputs of the reference functions on the same on-disk samples and stand-in encoder."""
+    import contextlib, io
+    import mmrs_b200.search as S
+    from conftest import GOLDEN
+    from golden_inputs import query_builder_setup
+    g = np.load(GOLDEN / "query_builders_golden.npz")
+    dataset_path, tower, preprocess, class_embeddings, class_to_idx, samples = query_builder_setup(str(tmp_path))
+    monkeypatch.setattr(S, "dataset_path", dataset_path)
+    monkeypatch.setattr(S, "class_to_idx", class_to_idx)
+    for cls in samples:
+        img_f, img_txt_f = S.get_image_text_features(tower, preprocess, class_embeddings.clone(), samples[cls], cls)
+        np.testing.assert_array_equal(img_f.numpy(), g[f"{cls}_image_features"])
+        np.testing.assert_array_equal(img_txt_f.numpy(), g[f"{cls}_image_text_features"])
+        feats = S._encode_samples(tower, preprocess, samples[cls], cls)
+        unit = (feats / feats.norm(dim=-1, keepdim=True)).numpy()
+        np.testing.assert_array_equal(S.outlier_filter_features(unit).numpy(), g[f"{cls}_outlier_filter"])
+        np.testing.assert_array_equal(oracle.outlier_filter_features(unit).numpy(), g[f"{cls}_outlier_filter"])
+    for cls, shots in (("alpha", 5), ("beta", 8)):
+        np.random.seed(0)
+        with contextlib.redirect_stdout(io.StringIO()):
+            got = S.get_cluster_features(tower, preprocess, samples[cls], shots, cls)
+        np.testing.assert_allclose(got.numpy(), g[f"{cls}_cluster_features"], atol=1e-7, rtol=0)
+
+
+def test_destructive_wrappers_validate_thresholds_without_a_gpu(mm, tmp_path):
+    """Argument checks run before anything touches the GPU or the files."""
+    (tmp_path / "x.png").write_bytes(b"not an image")
+    for bad in (0, 5, 0.5, 1.01, -1):
+        with pytest.raises(ValueError):
+            mm.find_and_remove_duplicate_images(str(tmp_path), bad)
+        with pytest.raises(ValueError):
+            mm.find_and_remove_duplicate_images(str(tmp_path), cosine_threshold=bad)
+        with pytest.raises(ValueError):
+            mm.find_and_remove_duplicate_images(str(tmp_path), str(tmp_path), threshold=bad)
+    with pytest.raises(ValueError):
+        mm.detect_and_remove_cross_set_duplicates(str(tmp_path), str(tmp_path), 8, 3)
+    with pytest.raises(TypeError):
+        mm.find_and_remove_duplicate_images(str(tmp_path), cosine_threshold="0.95")
+    assert os.path.exists(tmp_path / "x.png")
+
+
+def test_upload_cache_is_keyed_on_identity_not_address(mm, monkeypatch):
+    """get_similarity's one-entry upload cache must not serve a stale gallery to a NEW tensor that happens
+    to reuse a freed tensor's address (same shape, same dtype, _version 0)."""
+    import mmrs_b200.search as S
+    made = []
+
+    class FakeGallery:
+        def __init__(self, features, mode=None):
+            made.append(features)
+
+    monkeypatch.setattr(S, "DeviceGallery", FakeGallery)
+    S._last_upload.clear()
+    a = torch.randn(64, 8)
+    g1 = S._resident(a, None)
+    assert S._resident(a, None) is g1 and len(made) == 1           # same object, same version: reused
+    a.add_(1.0)
+    assert S._resident(a, None) is not g1 and len(made) == 2       # in-place edit: re-uploaded
+    ptr = a.data_ptr()
+    del a
+    b = torch.randn(64, 8)                                         # may or may not land on the old address
+    g3 = S._resident(b, None)
+    assert made[-1] is b and len(made) == 3
+    arr = np.zeros((4, 8), dtype=np.float32)
+    S._resident(arr, None); S._resident(arr, None)
+    assert len(made) == 5                                          # numpy inputs are never cached
+    S._last_upload.clear()
+    del ptr, g3

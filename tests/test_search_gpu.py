@@ -9,31 +9,42 @@ from golden_inputs import similarity_inputs
 pytestmark = pytest.mark.gpu
 
 
-def explain_index_mismatches(got_i, want_i, want_v, tol):
+def explain_index_mismatches(got_i, ext_i, ext_v, tol):
     """north_star: identical top-k indices, ties by index.  fp32 accumulation order differs between
     MKL and any GPU kernel, so a differing position is accepted ONLY if the
-    reference's own scores of the two rows involved lie within `tol`.  Returns #mismatches."""
-    bad = (got_i != want_i)
+    reference's own scores of the two rows involved lie within `tol`.  `ext_i` / `ext_v` are the
+    reference's top-(k+1) (k when the gallery has only k rows): position k - 1 is checked like every
+    other one -- the row returned there must be a reference near-tie of position k - 1 or k.
+    Returns #mismatches."""
+    k = got_i.shape[1]
+    assert ext_i.shape[1] >= k
+    bad = (got_i != ext_i[:, :k])
     n_bad = int(bad.sum())
     if n_bad == 0:
         return 0
     for q, j in zip(*np.nonzero(bad)):
         # the row we returned at position j must be one whose reference score is within tol of
         # the reference's j-th score
-        lo, hi = max(0, j - 8), min(want_v.shape[1], j + 9)
-        near = np.abs(want_v[q, lo:hi] - want_v[q, j]) <= tol
-        cand = set(want_i[q, lo:hi][near].tolist())
-        assert int(got_i[q, j]) in cand or j == want_v.shape[1] - 1, (q, j, got_i[q, j], want_i[q, j])
+        lo, hi = max(0, j - 8), min(ext_v.shape[1], j + 9)
+        near = np.abs(ext_v[q, lo:hi] - ext_v[q, j]) <= tol
+        cand = set(ext_i[q, lo:hi][near].tolist())
+        assert int(got_i[q, j]) in cand, (q, j, got_i[q, j], ext_i[q, j])
     return n_bad
 
 
+def oracle_topk_ext(oracle, q, g, k, **kw):
+    """(want_v [Q, k], want_i [Q, k], ext_v, ext_i [Q, min(k + 1, N)]) from the oracle."""
+    ext_v, ext_i = oracle.search_topk(q, g, min(k + 1, g.shape[0]), **kw)
+    return ext_v[:, :k].contiguous(), ext_i[:, :k].contiguous(), ext_v, ext_i
+
+
 def check_fp32(mm, oracle, g, q, k, max_swapped=0.005, **kw):
-    want_v, want_i = oracle.search_topk(q, g, k, mode="fp32", **kw)
+    want_v, want_i, ext_v, ext_i = oracle_topk_ext(oracle, q, g, k, mode="fp32", **kw)
     v, i = mm.search_topk(q, mm.DeviceGallery(g, mode="fp32"), k, **kw)
     assert v.shape == (q.shape[0], k) and i.dtype == torch.int64 and v.dtype == torch.float32
     scale = abs(kw.get("scale", 1.0))
     np.testing.assert_allclose(v.cpu().numpy(), want_v.numpy(), atol=1e-5 * max(scale, 1.0), rtol=0)
-    n_bad = explain_index_mismatches(i.cpu().numpy(), want_i.numpy(), want_v.numpy(), 1e-5 * max(scale, 1.0))
+    n_bad = explain_index_mismatches(i.cpu().numpy(), ext_i.numpy(), ext_v.numpy(), 1e-5 * max(scale, 1.0))
     assert n_bad <= max(1, int(i.numel() * max_swapped)), n_bad
     # descending, ties by ascending index
     vv, ii = v.cpu().numpy(), i.cpu().numpy()
@@ -203,12 +214,12 @@ def test_full_size_c2_small_batch(mm, oracle, nq):
     """C2 at full size: 1M x 512 bf16, top-100 (the oracle takes seconds for <= 4 queries)."""
     g = oracle.synthetic_gallery(1_000_000, 512, seed=0, dtype=torch.bfloat16)
     q = oracle.synthetic_queries(nq, 512, seed=1)
-    want_v, want_i = oracle.search_topk(q, g, 100, mode="bf16")
+    want_v, want_i, ext_v, ext_i = oracle_topk_ext(oracle, q, g, 100, mode="bf16")
     v, i = mm.search_topk(q, mm.DeviceGallery(g), 100)
     np.testing.assert_allclose(v.numpy(), want_v.numpy(), atol=1e-2, rtol=0)
     hits = sum(len(set(a) & set(b)) for a, b in zip(i.tolist(), want_i.tolist()))
     assert hits / want_i.numel() >= 0.999
-    assert explain_index_mismatches(i.numpy(), want_i.numpy(), want_v.numpy(), 1e-6) <= 2
+    assert explain_index_mismatches(i.numpy(), ext_i.numpy(), ext_v.numpy(), 1e-6) <= 2
 
 
 # ---- K2 (tcgen05) explicitly -----------------------------------------------------------------------
@@ -232,11 +243,11 @@ def check_bf16(mm, oracle, g, q, k, path, **kw):
         # ... then the strict comparison on identical bf16-valued operands
         q = bf16_unit_queries(q)
         kw = dict(kw, normalize_queries=False)
-    want_v, want_i = oracle.search_topk(q, g, k, mode="bf16", **kw)
+    want_v, want_i, ext_v, ext_i = oracle_topk_ext(oracle, q, g, k, mode="bf16", **kw)
     v, i = mm.search_topk(q, mm.DeviceGallery(g), k, path=path, **kw)
     v, i = v.cpu().numpy(), i.cpu().numpy()
     np.testing.assert_allclose(v, want_v.numpy(), atol=1e-5, rtol=0)       # far inside the 1e-2 of north_star
-    n_bad = explain_index_mismatches(i, want_i.numpy(), want_v.numpy(), 2e-6)
+    n_bad = explain_index_mismatches(i, ext_i.numpy(), ext_v.numpy(), 2e-6)
     hits = sum(len(set(a) & set(b)) for a, b in zip(i.tolist(), want_i.tolist()))
     assert hits / want_i.numel() >= 0.999
     assert np.all(v[:, 1:] <= v[:, :-1])
@@ -353,8 +364,8 @@ def test_c4_shard_size_12p5m_x_768(mm):
     gal = mm.DeviceGallery(data, row_offset=25_000_000)
     q = bf16_unit_queries(torch.randn(16, 768, generator=torch.Generator().manual_seed(3)))
     v, i = mm.search_topk(q, gal, 100, normalize_queries=False)
-    wv, wi = torch_gpu_topk(q, data, 100)
-    np.testing.assert_allclose(v.numpy(), wv.numpy(), atol=2e-6, rtol=0)
+    wv, wi = torch_gpu_topk(q, data, 101)
+    np.testing.assert_allclose(v.numpy(), wv[:, :100].numpy(), atol=2e-6, rtol=0)
     assert explain_index_mismatches(i.numpy() - 25_000_000, wi.numpy(), wv.numpy(), 2e-6) <= 8
     v1, i1 = mm.search_topk(q[:2], gal, 100, path="gemv", normalize_queries=False)
     assert (i1 == i[:2]).float().mean().item() > 0.99
@@ -367,10 +378,10 @@ def test_many_queries_super_chunks(mm, oracle):
     g = oracle.synthetic_gallery(120_000, 128, seed=12, dtype=torch.bfloat16)
     q = bf16_unit_queries(oracle.synthetic_queries(2500, 128, seed=13))
     v, i = mm.search_topk(q.cuda(), mm.DeviceGallery(g), 10, normalize_queries=False)
-    wv, wi = torch_gpu_topk(q, g.cuda(), 10)
-    np.testing.assert_allclose(v.cpu().numpy(), wv.numpy(), atol=2e-6, rtol=0)
+    wv, wi = torch_gpu_topk(q, g.cuda(), 11)
+    np.testing.assert_allclose(v.cpu().numpy(), wv[:, :10].numpy(), atol=2e-6, rtol=0)
     assert explain_index_mismatches(i.cpu().numpy(), wi.numpy(), wv.numpy(), 2e-6) <= 25
-    ov, oi = oracle.search_topk(q[:64], g, 10, mode="bf16", normalize_queries=False)
+    ov, oi = oracle.search_topk(q[:64], g, 11, mode="bf16", normalize_queries=False)
     assert explain_index_mismatches(i[:64].cpu().numpy(), oi.numpy(), ov.numpy(), 2e-6) <= 2
 
 
@@ -410,11 +421,11 @@ def test_fp32_tensor_core_path_matches_oracle(mm, oracle, n, d, nq, k):
     g = oracle.synthetic_gallery(n, d, seed=(n * 7 + d) % 83, dtype=torch.float32)
     q = oracle.synthetic_queries(nq, d, seed=nq + 1)
     gal = mm.DeviceGallery(g, mode="fp32")
-    want_v, want_i = oracle.search_topk(q, g, k, mode="fp32")
+    want_v, want_i, ext_v, ext_i = oracle_topk_ext(oracle, q, g, k, mode="fp32")
     v, i = mm.search_topk(q, gal, k)                       # >= 9 queries: split planes + tcgen05
     assert gal._split is not None
     np.testing.assert_allclose(v.numpy(), want_v.numpy(), atol=1e-5, rtol=0)
-    n_bad = explain_index_mismatches(i.numpy(), want_i.numpy(), want_v.numpy(), 1e-5)
+    n_bad = explain_index_mismatches(i.numpy(), ext_i.numpy(), ext_v.numpy(), 1e-5)
     assert n_bad <= max(1, i.numel() // 200)
     # the CUDA-core exact path agrees to fp32 rounding
     v1, i1 = mm.search_topk(q[:8], gal, k, path="gemv")
@@ -478,3 +489,175 @@ def test_overlap_grid_find_thresholds_golden(mm):
                 mm.find_thresholds(pos, neg, name, grid="overlap")
         else:
             assert mm.find_thresholds(pos, neg, name, grid="overlap") == g[f"{name}_best_f1"]
+
+
+# ---- round 2: graph cache keyed on the workspace slot, slots, float64 sweep, new mirrors --------------------
+def _graph_stats(mm):
+    import ctypes as C
+    out = (C.c_int64 * 4)()
+    mm._cabi.check(mm._cabi.lib.mmrs_graph_stats(out))
+    return {"captures": out[0], "replays": out[1], "patches": out[2], "unpatchable": out[3]}
+
+
+def test_retained_outputs_capture_once(mm, oracle):
+    """1 000 searches whose results (and queries) are all kept alive: every call brings new tensors, yet
+    the library captures ONE graph for the slot and only re-points its prep / final-select nodes."""
+    g = oracle.synthetic_gallery(60_000, 128, seed=3, dtype=torch.bfloat16)
+    gal = mm.DeviceGallery(g)
+    base = oracle.synthetic_queries(1000 * 4, 128, seed=8).cuda().view(1000, 4, 128)
+    mm.search_topk(base[0], gal, 10)                            # slot + first capture
+    s0 = _graph_stats(mm)
+    kept = [mm.search_topk(base[t], gal, 10) for t in range(1000)]
+    torch.cuda.synchronize()
+    s1 = _graph_stats(mm)
+    assert s1["captures"] == s0["captures"], (s0, s1)           # nothing was captured again
+    assert s1["unpatchable"] == s0["unpatchable"] == 0
+    assert s1["replays"] - s0["replays"] == 1000 and s1["patches"] - s0["patches"] >= 999
+    assert len({v.data_ptr() for v, _ in kept}) == 1000         # the results really are distinct live tensors
+    for t in (0, 1, 500, 999):                                  # and each holds ITS query's answer
+        wv, wi = oracle.search_topk(base[t].cpu(), g, 10, mode="bf16")
+        assert torch.equal(kept[t][1].cpu(), wi)
+    # out=: caller-owned result tensors, host staging keeps the host path on one graph too
+    v = torch.empty((4, 10), dtype=torch.float32, device="cuda"); i = torch.empty((4, 10), dtype=torch.int64, device="cuda")
+    rv, ri = mm.search_topk(base[7], gal, 10, out=(v, i))
+    assert rv is v and ri is i and torch.equal(i, kept[7][1])
+    hq = [base[t].cpu() for t in range(20)]
+    mm.search_topk(hq[0], gal, 10)
+    s2 = _graph_stats(mm)
+    host_kept = [mm.search_topk(q, gal, 10) for q in hq]
+    assert _graph_stats(mm)["captures"] == s2["captures"]
+    assert all(torch.equal(h[1], kept[t][1].cpu()) for t, h in enumerate(host_kept))
+    with pytest.raises(ValueError):
+        mm.search_topk(base[0], gal, 10, out=(v.cpu(), i.cpu()))
+
+
+def test_search_slots_are_capped(mm, oracle):
+    g = oracle.synthetic_gallery(5_000, 64, seed=3, dtype=torch.bfloat16)
+    gal = mm.DeviceGallery(g)
+    want = {}
+    for nq in range(1, 41):                                     # 40 batch sizes > MAX_SEARCH_SLOTS
+        q = oracle.synthetic_queries(nq, 64, seed=nq)
+        v, i = mm.search_topk(q.cuda(), gal, 5)
+        want[nq] = i.cpu()
+    slots = [k for k in gal._workspaces if k[0] == "search"]
+    assert len(slots) == gal.MAX_SEARCH_SLOTS
+    for nq in (1, 2, 40, 17):                                   # evicted and surviving shapes both still work
+        q = oracle.synthetic_queries(nq, 64, seed=nq)
+        assert torch.equal(mm.search_topk(q.cuda(), gal, 5)[1].cpu(), want[nq])
+    # a search workspace no longer carries the exhaustive buffer (8 bytes per row)
+    lib = mm._cabi.lib
+    small = lib.mmrs_search_workspace_bytes(100_000_000, 768, 1, 16, 100)
+    assert small < 64 << 20 and lib.mmrs_search_exhaustive_workspace_bytes(100_000_000, 768, 16) > 800_000_000
+
+
+def test_threshold_sweep_float64_scores(mm):
+    """float64 scores are compared in float64 (numpy's compare), never rounded to float32 first."""
+    rng = np.random.default_rng(3)
+    base = rng.normal(20, 3, 5000)
+    pos = base[:1000].copy(); neg = base[1000:].copy()
+    thr = np.linspace(base.min(), base.max(), 200)
+    # plant scores a hair below / above grid points: rounding them to float32 would move them across
+    for j in range(10, 190, 7):
+        pos[j] = np.nextafter(thr[j], -np.inf)
+        neg[j] = np.nextafter(thr[j], np.inf)
+    tp, fp = mm.threshold_sweep_counts(pos, neg, thr)
+    np.testing.assert_array_equal(tp, [(pos >= t).sum() for t in thr])
+    np.testing.assert_array_equal(fp, [(neg >= t).sum() for t in thr])
+    tp32, _ = mm.threshold_sweep_counts(pos.astype(np.float32), neg.astype(np.float32), thr)
+    assert not np.array_equal(tp32, tp)                           # the float32 path WOULD differ on this data
+    # the drop-ins take python lists / float64 arrays like the reference does
+    f1 = mm.find_thresholds(list(pos), list(neg), "f64")
+    import oracle.oracle as O
+    assert f1 == O.find_thresholds(pos, neg)[0]
+    got = mm.eval_threshold(pos, neg, float(thr[17]))
+    assert tuple(got) == tuple(O.eval_threshold(pos, neg, float(thr[17])))
+
+
+def test_cls_acc_and_topk_of_scores_golden(mm, oracle):
+    """cls_acc (code/utils.py:15-39) on the GPU select kernel against the reference's recorded accuracies."""
+    from golden_inputs import topk_inputs
+    gold = np.load(GOLDEN / "utils_topk_golden.npz")
+    for name, (logits, target) in topk_inputs().items():
+        for k in (1, 3):
+            v, i = mm.topk_of_scores(logits, k)
+            wv, wi = oracle.topk_rows(logits, k)
+            assert torch.equal(v, wv) and torch.equal(i, wi)            # values exact, ties by ascending index
+            np.testing.assert_array_equal(v.numpy(), gold[f"{name}_topk{k}_values"])
+            if name == "random":                                         # no ties: indices equal torch.topk's too
+                np.testing.assert_array_equal(i.numpy(), gold[f"{name}_topk{k}_indices"])
+                assert mm.cls_acc(logits, target, topk=k) == float(gold[f"{name}_acc_k{k}"])
+                assert mm.cls_acc(logits.cuda(), target.cuda(), topk=k) == float(gold[f"{name}_acc_k{k}"])
+    logits, target = topk_inputs()["random"]
+    keep = target != 2
+    want = 100 * float((logits.argmax(1) == target)[keep].float().sum()) / int(keep.sum())
+    assert mm.cls_acc(logits, target, 1, exclude_class=2) == want
+    assert mm.cls_acc(logits[:3], torch.full((3,), 4), 1, exclude_class=4) == 0.0
+    big = torch.randn(257, 1000, generator=torch.Generator().manual_seed(1))
+    v, i = mm.topk_of_scores(big.cuda(), 5)
+    wv, wi = oracle.topk_rows(big, 5)
+    assert torch.equal(i.cpu(), wi) and torch.equal(v.cpu(), wv)
+    with pytest.raises(RuntimeError, match="out of range"):
+        mm.topk_of_scores(logits, 7)
+
+
+def test_cosine_similarity_scores_golden(mm):
+    """logit_scale * F.cosine_similarity (code/merge_dataset.py:275-278) through the gallery scan, against
+    the similarity and the thresholded predictions recorded from the reference's clip_en_predict."""
+    from golden_inputs import cosine_inputs
+    gold = np.load(GOLDEN / "merge_dataset_golden.npz")
+    x, t, logit_scale = cosine_inputs()
+    got = mm.cosine_similarity_scores(x, t, logit_scale)
+    assert got.shape == (300,) and not got.is_cuda
+    np.testing.assert_allclose(got.numpy(), gold["similarity"], atol=1e-3, rtol=0)      # scale 100: 1e-5 on the cosine
+    for thr in (-3.0, 0.0, 2.5, 70.0):
+        pred = (got.numpy() < thr).astype(np.int64)
+        far = np.abs(gold["similarity"] - thr) > 1e-3
+        np.testing.assert_array_equal(pred[far], gold[f"preds_{thr:g}"][far])
+        assert far.mean() > 0.98
+    # torch's clamp semantics: a zero row scores 0 (the x / x.norm() idiom would give NaN)
+    xz = x.clone(); xz[5] = 0
+    gz = mm.cosine_similarity_scores(xz.cuda(), t.cuda(), 100.0)
+    want = 100.0 * torch.nn.functional.cosine_similarity(xz, t)
+    assert gz.is_cuda and float(gz[5]) == 0.0
+    np.testing.assert_allclose(gz.cpu().numpy(), want.numpy(), atol=1e-3, rtol=0)
+    with pytest.raises(ValueError):
+        mm.cosine_similarity_scores(x, torch.cat([t, t]), 1.0)
+
+
+def test_config_c1_literal_random_init_vit_b32(mm, oracle):
+    """BASELINE.json configs[0] on its literal inputs: the gallery is 10 000 image features of a random-init
+    ViT-B/32 (transformers.CLIPModel(CLIPConfig()), torch.manual_seed(1) -- the reference's seed,
+    code/search_image.py:323-324 -- on randn images), the 100 queries are text features of random token ids;
+    rows unit-normalised; top-10 cosine in fp32 mode through BOTH fp32 paths (K1 CUDA cores, bf16x3 tensor cores)
+    against the torch CPU oracle.  Random-init features are nearly collinear, so many scores are
+    near-ties: a differing index is accepted only if the reference's own scores of the rows lie within 1e-5."""
+    transformers = pytest.importorskip("transformers")
+    torch.manual_seed(1)
+    model = transformers.CLIPModel(transformers.CLIPConfig()).eval().cuda()
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    feats = []
+    with torch.no_grad():
+        for _ in range(20):
+            imgs = torch.randn((500, 3, 224, 224), generator=gen, device="cuda")
+            f = model.get_image_features(pixel_values=imgs)
+            f = f if isinstance(f, torch.Tensor) else f.pooler_output
+            feats.append(f.float())
+        ids = torch.randint(0, 49407, (100, 77), generator=gen, device="cuda")
+        t = model.get_text_features(input_ids=ids)
+        t = (t if isinstance(t, torch.Tensor) else t.pooler_output).float()
+    g = torch.cat(feats)
+    g = (g / g.norm(dim=-1, keepdim=True)).cpu()                 # build_cache, search_image.py:157
+    q = t.cpu()
+    del model, feats
+    torch.cuda.empty_cache()
+    assert g.shape == (10_000, 512) and q.shape == (100, 512) and torch.isfinite(g).all()
+    want_v, want_i, ext_v, ext_i = oracle_topk_ext(oracle, q, g, 10, mode="fp32")
+    gal = mm.DeviceGallery(g, mode="fp32")
+    spread = float(ext_v[:, 0].mean() - ext_v[:, -1].mean())
+    for path in ("gemv", "auto"):
+        v, i = mm.search_topk(q, gal, 10, path=path)
+        np.testing.assert_allclose(v.numpy(), want_v.numpy(), atol=1e-5, rtol=0)
+        n_bad = explain_index_mismatches(i.numpy(), ext_i.numpy(), ext_v.numpy(), 1e-5)
+        print(f"C1 literal ({path}): {n_bad} near-tie index differences of 1000; top-1..11 score spread {spread:.2e}")
+        assert n_bad <= 100
+    assert gal._split is not None                                # "auto" at 100 queries ran the tensor-core fp32 path
