@@ -81,8 +81,10 @@ def measured_peaks():
 
 class ClockSampler:
     """SM clock and throttle reasons sampled DURING a timed region, in-process through NVML (the
-    nvidia-smi child of round 1 needed longer to start than a short region lasts).  One sample is
-    taken synchronously on entry and on exit, so that every region has a record."""
+    nvidia-smi child of round 1 needed longer to start than a short region lasts): a thread samples
+    every 20 ms (an NVML query is a driver round trip that can delay kernel launches -- per-step
+    queries slowed 0.2 ms steps measurably, so the timing loop itself never calls NVML), plus one
+    synchronous sample at the end of the region, so that every region has a record."""
 
     def __init__(self, torch, device):
         self.samples, self.reason_bits, self.max_mhz = [], 0, None
@@ -111,7 +113,7 @@ class ClockSampler:
             pass
 
     def _loop(self):
-        while not self._stop.wait(0.004):
+        while not self._stop.wait(0.02):
             self._one()
 
     def __enter__(self):
@@ -144,7 +146,7 @@ class ClockSampler:
         sm = sorted(self.samples)
         return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.max_mhz,
                 "reasons": [n for n, bit in names if self.reason_bits & bit], "samples": len(sm),
-                "how": "NVML in-process, 4 ms period, during the timed region"}
+                "how": "NVML in-process, 20 ms period + one sample at the end, during the timed region"}
 
 
 def device_gallery_shard(torch, rows, dim, seed, shard_id, device):
@@ -276,8 +278,6 @@ class Bench:
                 inflight.append(fn(sync=False))
             if len(inflight) >= self.DEPTH:
                 out = inflight.pop(0).wait()
-                if clocks is not None:
-                    clocks.mark()
         for pnd in inflight:
             out = pnd.wait()
         return out

@@ -41,7 +41,8 @@ constexpr int kBlockM = kTileRows;       // gallery rows per tile == UMMA M
 constexpr int kBlockK = 64;              // bf16 elements per k-block == one 128-byte swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kMaxQ = 256;               // UMMA N limit
-constexpr int kSplitMaxQ = 48;           // fp32 emulation: queries per pass (3 x (16 + 6) KB per stage, 3 stages)
+constexpr int kSplitMaxQ = 48;           // fp32 emulation, single CTA: queries per pass (3 x (16 + 6) KB per stage, 3 stages)
+constexpr int kSplitPairMaxQ = 128;      // fp32 emulation as CTA pairs: each CTA stages half the query rows of every plane
 constexpr int kMaxQChunks = 4;           // query chunks of kMaxQ that may share the gallery stream of one launch
 constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KiB
 constexpr int kMaxStages = 8;
@@ -72,6 +73,8 @@ struct MmaCfg {
   int32_t q_plane_rows;  // split == 3: rows between two planes of the prepared queries
   int32_t debug_skip_epilogue;   // measurement aid (MMRS_K2_DEBUG_SKIP_EPI=1): results are garbage
   int32_t n_qchunks;     // pair mode: query chunks of kMaxQ in this launch (they are work units, not gridDim.y)
+  int32_t sticky;        // pair mode, several chunks, many tiles: a pair scans ALL chunks of its tile pair back to back
+  int32_t prefetch;      // TMA-prefetch the gallery tile of the NEXT unit into L2 while this unit's tile is loaded
 };
 
 
@@ -113,14 +116,27 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   const int R = PAIR ? plan_exclusion_ratio(inc, exc) : 0;
   const int n_valid = plan_n_visited(p.sched.n_sel, R);
+  // Sticky order (several chunks, many tiles -- the tensor-bound 64K-query batches): the pair takes tile
+  // pairs tp = pair, pair + n_pairs, ... and scans all n_ch chunks of one tile pair back to back, so the
+  // three re-reads of a gallery tile come from L2 BY CONSTRUCTION (the same SM pair asks again a few
+  // microseconds later) instead of relying on four different pairs staying in step: the interleaved order
+  // read every tile from DRAM about twice (dram read 5.86 GB for 2.98 GB of gallery, L2 hit rate 70 %,
+  // profiles/r01_k2_c5like_pair2_summary.txt).
   const int n_ch = PAIR ? cfg.n_qchunks : 1;
-  const int u_begin = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-  const int u_step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
-  const int n_units = PAIR ? plan_pair_units(n_valid, n_ch) : p.sched.n_sel;
+  const bool sticky = PAIR && cfg.sticky != 0;
+  const int n_pairs_grid = static_cast<int>(gridDim.x >> 1), pair_id = static_cast<int>(blockIdx.x >> 1);
+  const int u_begin = PAIR ? (sticky ? 0 : pair_id) : static_cast<int>(blockIdx.x);
+  const int u_step = PAIR ? (sticky ? 1 : n_pairs_grid) : static_cast<int>(gridDim.x);
+  const int n_tile_pairs = (n_valid + 1) / 2;
+  const int n_units = PAIR ? (sticky ? (pair_id < n_tile_pairs ? ((n_tile_pairs - pair_id + n_pairs_grid - 1) / n_pairs_grid) * n_ch : 0)
+                                     : plan_pair_units(n_valid, n_ch))
+                           : p.sched.n_sel;
   struct Unit { int j, chunk; bool valid, skip; };
   auto unit_of = [&](int u) -> Unit {
     if constexpr (PAIR) {
-      const PairUnit pu = plan_pair_unit(u, static_cast<int>(rank), n_ch, n_valid, R);   // plan.h
+      // sticky: u counts this pair's own units; u / n_ch-th tile pair of the pair, chunk u % n_ch
+      const int gu = sticky ? (pair_id + (u / n_ch) * n_pairs_grid) * n_ch + u % n_ch : u;
+      const PairUnit pu = plan_pair_unit(gu, static_cast<int>(rank), n_ch, n_valid, R);   // plan.h
       return Unit{pu.j, pu.chunk, pu.valid, false};
     } else {
       return Unit{u, static_cast<int>(blockIdx.y), true, exc != 0 && ((u * inc) % exc) == 0};
@@ -191,6 +207,20 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
         if (un.skip) continue;
         const int32_t row0 = un.j * inc * kBlockM;
         const int32_t qrow0 = p.q0 + un.chunk * kMaxQ + static_cast<int>(rank) * b_rows;
+        if (cfg.prefetch) {
+          // the next unit this CTA will load a NEW gallery tile for (sticky: the chunks of a tile pair re-read it)
+          int u2 = u + u_step;
+          while (u2 < n_units && unit_of(u2).skip) u2 += u_step;
+          if (u2 < n_units) {
+            const Unit nx = unit_of(u2);
+            if (nx.j != un.j) {
+              const int32_t nrow0 = nx.j * inc * kBlockM;
+              for (int pl = 0; pl < cfg.split; ++pl)
+                for (int kb = 0; kb < cfg.k_blocks; ++kb)
+                  tma_prefetch_2d(&map_g, kb * kBlockK, static_cast<int32_t>(pl * cfg.g_plane_rows) + nrow0);
+            }
+          }
+        }
         for (int kb = 0; kb < cfg.k_blocks; ++kb) {
           if (!mbar_wait(&sh->empty[stage], phase ^ 1, &sh->abort, flags)) { ok = false; break; }
           uint8_t* a_dst = ring + static_cast<size_t>(stage) * stage_bytes;
@@ -198,8 +228,13 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
             // both halves of the stage are credited to the LEADER's barrier, which its MMA warp waits on
             const uint32_t full_leader = mapa_u32(smem_u32(&sh->full[stage]), 0);
             if (rank == 0) mbar_expect_tx(&sh->full[stage], 2 * stage_bytes);
-            tma_load_2d_pair(a_dst, &map_g, full_leader, kb * kBlockK, row0, kEvictFirst);
-            tma_load_2d_pair(a_dst + kABytes, &map_q, full_leader, kb * kBlockK, qrow0, kEvictLast);
+            const uint64_t a_hint = sticky ? (un.chunk == n_ch - 1 ? kEvictFirst : kEvictNormal) : kEvictFirst;
+            for (int pl = 0; pl < cfg.split; ++pl) {
+              tma_load_2d_pair(a_dst + pl * kABytes, &map_g, full_leader, kb * kBlockK,
+                               static_cast<int32_t>(pl * cfg.g_plane_rows) + row0, a_hint);
+              tma_load_2d_pair(a_dst + a_all + pl * b_bytes, &map_q, full_leader, kb * kBlockK,
+                               pl * cfg.q_plane_rows + qrow0, kEvictLast);
+            }
           } else {
             mbar_expect_tx(&sh->full[stage], stage_bytes);
             for (int pl = 0; pl < cfg.split; ++pl) {
@@ -236,7 +271,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
           tcgen05_fence_after();
           const uint32_t a_addr = ring_addr + stage * stage_bytes;
           if (elect_one()) {
-            if (PAIR || cfg.split == 1) {
+            if (cfg.split == 1) {
               const uint64_t adesc = make_sw128_desc(a_addr);
               const uint64_t bdesc = make_sw128_desc(a_addr + kABytes);
 #pragma unroll
@@ -261,9 +296,14 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
                 const uint64_t adesc = make_sw128_desc(a_addr + kTermA[term] * kABytes);
                 const uint64_t bdesc = make_sw128_desc(a_addr + a_all + kTermB[term] * b_bytes);
 #pragma unroll
-                for (int k = 0; k < kBlockK / kUmmaK; ++k)
-                  umma_bf16(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
-                            (kb | k | term) != 0 ? 1u : 0u);
+                for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                  if constexpr (PAIR)
+                    umma_bf16_pair(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
+                                   (kb | k | term) != 0 ? 1u : 0u);
+                  else
+                    umma_bf16(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
+                              (kb | k | term) != 0 ? 1u : 0u);
+                }
               }
             }
             // smem slot reusable (in both CTAs of a pair) once these MMAs retire
@@ -452,7 +492,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
   }
 }
 
-int scan_mma_split_max_queries() { return kSplitMaxQ; }
+int scan_mma_split_max_queries() { return getenv("MMRS_K2_NO_PAIR") ? kSplitMaxQ : kSplitPairMaxQ; }
 int scan_mma_max_queries() {
   const char* e = getenv("MMRS_K2_QCHUNKS");
   const int c = e ? atoi(e) : kMaxQChunks;
@@ -465,7 +505,7 @@ cudaError_t launch_scan_mma(const ScanParams& p, const __nv_bfloat16* q_bf16, in
   const int n_qchunks = (p.nq + kMaxQ - 1) / kMaxQ;
   if (p.nq < 1 || n_qchunks > kMaxQChunks) return cudaErrorInvalidValue;
   if (split != 1 && split != 3) return cudaErrorInvalidValue;
-  if (split == 3 && p.nq > kSplitMaxQ) return cudaErrorInvalidValue;
+  if (split == 3 && p.nq > scan_mma_split_max_queries()) return cudaErrorInvalidValue;
   if (p.n_rows > 0x7fffffffll - kBlockM) return cudaErrorInvalidValue;   // TMA coordinates are int32
   if (p.sched.tile_exc != 0 && p.sched.tile_exc % p.sched.tile_inc != 0) return cudaErrorInvalidValue;
   MmaCfg cfg;
@@ -475,6 +515,13 @@ cudaError_t launch_scan_mma(const ScanParams& p, const __nv_bfloat16* q_bf16, in
   cfg.g_plane_rows = p.n_rows;
   cfg.q_plane_rows = n_q_padded;
   cfg.n_qchunks = n_qchunks;
+  cfg.sticky = 0;
+  // The ring holds about one tile per CTA (8 x 16 KB); its slots turn around once per DRAM latency PLUS the time
+  // the MMAs of the slot take, so with more queries the bytes in flight per SM stop covering the loaded HBM
+  // latency (kernel 0.151 ms at 16 queries -> 0.174 at 128, and proportional to the SM count).  L2 prefetches
+  // need no shared-memory slot: the next unit's tile is requested one unit (~3 us) ahead and the ring's own
+  // loads then hit L2.  DRAM traffic is unchanged (19 MB outstanding against 126 MB of L2).
+  cfg.prefetch = getenv("MMRS_K2_PREFETCH") ? atoi(getenv("MMRS_K2_PREFETCH")) : 1;
   cfg.debug_skip_epilogue = getenv("MMRS_K2_DEBUG_SKIP_EPI") ? atoi(getenv("MMRS_K2_DEBUG_SKIP_EPI")) : 0;   // 1: no epilogue, 2: nothing passes
   // Up to 64 queries the CTA is sized so that TWO fit on an SM (<= 113 KB of shared memory, 80
   // registers x 384 threads, <= 256 TMEM columns each): the scans of two searches in flight on
@@ -488,7 +535,10 @@ cudaError_t launch_scan_mma(const ScanParams& p, const __nv_bfloat16* q_bf16, in
   // Above that the kernel runs as CTA pairs (cta_group::2, see the file header)
   int pair_min = 64;
   if (const char* e = getenv("MMRS_K2_PAIR_MIN")) pair_min = atoi(e);
-  const bool pair = !small && split == 1 && cfg.n_umma > pair_min && getenv("MMRS_K2_NO_PAIR") == nullptr;
+  // fp32 emulation: up to 48 queries a single CTA per SM holds three stages of all six planes; beyond that the
+  // pair halves the query planes per CTA, so that 100 queries (BASELINE C1) are ONE pass over the gallery
+  // planes instead of three (1.49 ms -> one 3 GB stream at 1M x 512, profiles/r02_fp32_bench_*.log)
+  const bool pair = !small && (split == 1 ? cfg.n_umma > pair_min : p.nq > kSplitMaxQ) && getenv("MMRS_K2_NO_PAIR") == nullptr;
   if (pair) cfg.n_umma = (cfg.n_umma + 31) / 32 * 32;   // each CTA stages half the query rows
   int cols = 32;
   while (cols < 2 * cfg.n_umma) cols <<= 1;
@@ -521,8 +571,18 @@ cudaError_t launch_scan_mma(const ScanParams& p, const __nv_bfloat16* q_bf16, in
     // one pair per TPC; units = (tile pair, query chunk)
     const int n_units = plan_pair_units(n_valid, n_qchunks);
     int pairs = sm_count / 2;
+    // Measured and rejected (profiles/r02_hbm_pairs_ab.log): running HBM-bound pair launches on 64 or 56 of the 74
+    // TPCs, to leave SMs to the second search in flight, slows the scan in proportion (0.174 -> 0.196 -> 0.218 ms
+    // at 128 queries): the scan is bound by bytes in flight per SM, not by HBM alone.  The knob stays for A/B runs.
+    int hbm_pairs = 0;
+    if (const char* e = getenv("MMRS_K2_HBM_PAIRS")) hbm_pairs = atoi(e);
+    if (split == 1 && n_qchunks == 1 && cfg.n_umma <= 128 && n_units >= 8 * pairs && hbm_pairs >= 8 && hbm_pairs < pairs)
+      pairs = hbm_pairs;
     if (pairs > n_units) pairs = n_units;
     grid = dim3(2 * pairs, 1);
+    // every pair gets at least four tile pairs of its own: the chunks of a tile pair can stay on one pair
+    const char* st = getenv("MMRS_K2_STICKY");
+    cfg.sticky = (st ? atoi(st) != 0 : true) && n_qchunks > 1 && (n_valid + 1) / 2 >= 4 * pairs;
   } else {
     // 33..64 queries: the small-footprint CTA has only 4 ring stages, so one launch fills both CTA
     // slots of every SM itself (measured: 0.202 vs 0.224 ms per step at 64 queries)

@@ -64,6 +64,12 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "r"(c1), "l"(cache_hint)
       : "memory");
 }
+// request a tile into L2 only (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -163,6 +169,7 @@ __host__ __device__ constexpr uint32_t make_idesc(uint32_t n, uint32_t m = 128u)
 
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;   // gallery: streamed once
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;    // queries: re-read by every tile
+constexpr uint64_t kEvictNormal = 0x1000000000000000ull;  // gallery tile that the same SM pair re-reads for the next query chunk
 
 // ---- host side ---------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

@@ -20,6 +20,13 @@ sg = mmrs_b200.ShardedGallery.from_full(g, device=dev)
 sg_nccl = mmrs_b200.ShardedGallery(sg.local, n, fused=False)
 
 
+def unit_bf16(q):
+    """Normalised and rounded to bf16 once, on the host: with more than ~100 queries the fused normalisation's
+    last-ulp differences from torch flip a bf16 query element now and then (scores move by ~1e-4, inside
+    north_star's 1e-2, outside the 1e-5 checked here) -- see tests/test_search_gpu.py::bf16_unit_queries."""
+    return (q / q.norm(dim=-1, keepdim=True)).to(torch.bfloat16).to(torch.float32)
+
+
 def near_equal(i, v, wi, wv, max_bad):
     bad = (i.cpu() != wi)
     assert int(bad.sum()) <= max_bad, (rank, int(bad.sum()))
@@ -30,10 +37,13 @@ def near_equal(i, v, wi, wv, max_bad):
 
 for nq in (3, 24, 130):
     q = oracle.synthetic_queries(nq, d, seed=nq)
-    v, i = sg.search_topk(q.to(dev), k)
-    wv, wi = oracle.search_topk(q, g, k, mode="bf16")
+    norm = nq < 100
+    if not norm:
+        q = unit_bf16(q)
+    v, i = sg.search_topk(q.to(dev), k, normalize_queries=norm)
+    wv, wi = oracle.search_topk(q, g, k, mode="bf16", normalize_queries=norm)
     near_equal(i, v, wi, wv, 2 + nq // 16)
-    vb, ib = sg_nccl.search_topk(q.to(dev), k)
+    vb, ib = sg_nccl.search_topk(q.to(dev), k, normalize_queries=norm)
     assert torch.equal(i, ib) and torch.equal(v, vb)          # fused and NCCL variants agree bit for bit
 assert sg.fused_active and not sg_nccl.fused_active, "the fused NVLink gather was not used"
 
@@ -55,17 +65,17 @@ for t in (0, 49):
 # two streams x several batches in flight with MORE queries than SMs: the merge selects of the two slots
 # must not starve each other's scans across ranks (the waits run in one-warp kernels)
 streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
-qs = [oracle.synthetic_queries(300, d, seed=40 + t) for t in range(6)]
+qs = [unit_bf16(oracle.synthetic_queries(300, d, seed=40 + t)) for t in range(6)]
 qd = [x.to(dev) for x in qs]
 torch.cuda.synchronize()
 pends = []
 for t in range(6):
     streams[t % 2].wait_stream(torch.cuda.current_stream(dev))
     with torch.cuda.stream(streams[t % 2]):
-        pends.append(sg.search_topk(qd[t], k, sync=False))
+        pends.append(sg.search_topk(qd[t], k, sync=False, normalize_queries=False))
 outs = [p.wait() for p in pends]
 for t in (0, 5):
-    wv, wi = oracle.search_topk(qs[t], g, k, mode="bf16")
+    wv, wi = oracle.search_topk(qs[t], g, k, mode="bf16", normalize_queries=False)
     near_equal(outs[t][1], outs[t][0], wi, wv, 40)
 torch.cuda.synchronize()
 
