@@ -401,23 +401,28 @@ class Bench:
         how = ("CUDA events around every launch of the kernel, on the launching stream, "
                f"{prof_steps} steps re-run with the library's profiling hooks enabled")
         shape = f"{rows_local}x{dim}q{nq}"
-        traffic = None
-        tpath = ROOT / "profiles" / "traffic.json"       # dram bytes of ncu --set full captures, keyed by kernel@shape
+        traffic, traffic_src = None, None
+        tpath = ROOT / "profiles" / "traffic.json"       # dram bytes of ncu --set full captures, keyed kernel@shape
         if tpath.exists():
-            tj = json.loads(tpath.read_text()).get(f"{kname}@{shape}")
-            if tj:
-                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+            for key, tj in json.loads(tpath.read_text()).items():
+                if not key.startswith(kname + "@"):
+                    continue
+                r_, rest = key.split("@")[1].split("x")
+                d_, q_ = rest.split("q")
+                if int(d_) == dim and int(q_) == nq and abs(int(r_) - rows_local) <= 1e-3 * rows_local:
+                    traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+                    traffic_src = f"{tj['source']}, captured at {key.split('@')[1]}"
         if min(nq, 256) >= 224:     # past the ridge (Q* ~ 206-248): tensor-bound
             long_step = ms_per_step > 50.0
             tpk = pk["tc_sustained"] if long_step else pk["tc"]
-            return {"bound": "tensor", "achieved": tfl, "peak": tpk, "unit": "TFLOP/s", "frac": tfl / tpk, "traffic": traffic,
+            return {"bound": "tensor", "achieved": tfl, "peak": tpk, "unit": "TFLOP/s", "frac": tfl / tpk, "traffic": traffic, "traffic_source": traffic_src,
                     "peak_source": f"{pk['src']} bf16_tflops{'_sustained (step > 50 ms: runs against the power cap)' if long_step else ' (burst)'}",
                     "kernel": kname, "shape": shape, "algorithmic_flops_per_launch": dom[0][3], "avg_launch_ms": avg_ms,
                     "launches_timed": len(dom), "hbm_gbs": gbs,
                     "whole_step_tflops_per_gpu": 2.0 * nq * rows_local * dim / (ms_per_step / 1e3) / 1e12,
                     "frac_of_burst": tfl / pk["tc"], "how": how}
         return {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
-                "traffic": traffic, "peak_source": f"{pk['src']} hbm_gbs (burst copy)", "kernel": kname, "shape": shape,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": f"{pk['src']} hbm_gbs (burst copy)", "kernel": kname, "shape": shape,
                 "algorithmic_bytes_per_launch": big, "avg_launch_ms": avg_ms, "launches_timed": len(dom), "tflops": tfl,
                 "scan_kernels_ms_per_step": scan_ms, "share_of_step": scan_ms / ms_per_step,
                 "whole_step_frac": (rows_local * dim * 2) / (ms_per_step / 1e3) / 1e9 / pk["hbm"], "how": how}

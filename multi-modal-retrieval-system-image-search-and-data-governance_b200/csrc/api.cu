@@ -134,6 +134,7 @@ bool pdl_enabled() {
   return on;
 }
 
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 static int env_int(const char* name, int dflt) {

@@ -79,7 +79,10 @@ struct MmaCfg {
 
 
 
-template <int MODE, int EPI_WARPS, bool PAIR>
+// SPLIT is a template parameter on purpose: with the operand-plane count a run-time value the single lane that
+// issues tcgen05.mma carried both code paths and the C5-shaped scan fell from 4.11 back to 4.67 ms per launch
+// (profiles/r02_prefetch_ab.log against r02_sticky_ab.log) -- that loop is issue-bound, every instruction counts.
+template <int MODE, int EPI_WARPS, bool PAIR, int SPLIT>
 __global__ void __launch_bounds__((kCtrlWarps + EPI_WARPS) * 32, EPI_WARPS == 8 ? 2 : 1)
 scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_q,
                 const ScanParams p, const MmaCfg cfg, int32_t* flags) {
@@ -92,8 +95,8 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
   const uint32_t b_bytes = static_cast<uint32_t>(b_rows) * kBlockK * 2;
   // split == 3 (fp32 emulation): a stage holds the hi/mid/lo planes of both operands,
   // [A_hi | A_mid | A_lo | B_hi | B_mid | B_lo]
-  const uint32_t a_all = static_cast<uint32_t>(cfg.split) * kABytes;
-  const uint32_t stage_bytes = static_cast<uint32_t>(cfg.split) * (kABytes + b_bytes);
+  const uint32_t a_all = static_cast<uint32_t>(SPLIT) * kABytes;
+  const uint32_t stage_bytes = static_cast<uint32_t>(SPLIT) * (kABytes + b_bytes);
   Shared* sh = reinterpret_cast<Shared*>(ring + static_cast<size_t>(cfg.stages) * stage_bytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -215,7 +218,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
             const Unit nx = unit_of(u2);
             if (nx.j != un.j) {
               const int32_t nrow0 = nx.j * inc * kBlockM;
-              for (int pl = 0; pl < cfg.split; ++pl)
+              for (int pl = 0; pl < SPLIT; ++pl)
                 for (int kb = 0; kb < cfg.k_blocks; ++kb)
                   tma_prefetch_2d(&map_g, kb * kBlockK, static_cast<int32_t>(pl * cfg.g_plane_rows) + nrow0);
             }
@@ -229,7 +232,8 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
             const uint32_t full_leader = mapa_u32(smem_u32(&sh->full[stage]), 0);
             if (rank == 0) mbar_expect_tx(&sh->full[stage], 2 * stage_bytes);
             const uint64_t a_hint = sticky ? (un.chunk == n_ch - 1 ? kEvictFirst : kEvictNormal) : kEvictFirst;
-            for (int pl = 0; pl < cfg.split; ++pl) {
+#pragma unroll
+            for (int pl = 0; pl < SPLIT; ++pl) {
               tma_load_2d_pair(a_dst + pl * kABytes, &map_g, full_leader, kb * kBlockK,
                                static_cast<int32_t>(pl * cfg.g_plane_rows) + row0, a_hint);
               tma_load_2d_pair(a_dst + a_all + pl * b_bytes, &map_q, full_leader, kb * kBlockK,
@@ -237,7 +241,8 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
             }
           } else {
             mbar_expect_tx(&sh->full[stage], stage_bytes);
-            for (int pl = 0; pl < cfg.split; ++pl) {
+#pragma unroll
+            for (int pl = 0; pl < SPLIT; ++pl) {
               tma_load_2d(a_dst + pl * kABytes, &map_g, &sh->full[stage], kb * kBlockK,
                           static_cast<int32_t>(pl * cfg.g_plane_rows) + row0, kEvictFirst);
               tma_load_2d(a_dst + a_all + pl * b_bytes, &map_q, &sh->full[stage], kb * kBlockK,
@@ -271,7 +276,7 @@ scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant
           tcgen05_fence_after();
           const uint32_t a_addr = ring_addr + stage * stage_bytes;
           if (elect_one()) {
-            if (cfg.split == 1) {
+            if constexpr (SPLIT == 1) {
               const uint64_t adesc = make_sw128_desc(a_addr);
               const uint64_t bdesc = make_sw128_desc(a_addr + kABytes);
 #pragma unroll
@@ -516,12 +521,14 @@ cudaError_t launch_scan_mma(const ScanParams& p, const __nv_bfloat16* q_bf16, in
   cfg.q_plane_rows = n_q_padded;
   cfg.n_qchunks = n_qchunks;
   cfg.sticky = 0;
-  // The ring holds about one tile per CTA (8 x 16 KB); its slots turn around once per DRAM latency PLUS the time
-  // the MMAs of the slot take, so with more queries the bytes in flight per SM stop covering the loaded HBM
-  // latency (kernel 0.151 ms at 16 queries -> 0.174 at 128, and proportional to the SM count).  L2 prefetches
-  // need no shared-memory slot: the next unit's tile is requested one unit (~3 us) ahead and the ring's own
-  // loads then hit L2.  DRAM traffic is unchanged (19 MB outstanding against 126 MB of L2).
-  cfg.prefetch = getenv("MMRS_K2_PREFETCH") ? atoi(getenv("MMRS_K2_PREFETCH")) : 1;
+  // Idea: the ring holds about one tile per CTA (8 x 16 KB); its slots turn around once per DRAM latency PLUS
+  // the time the MMAs of the slot take, so with more queries the bytes in flight per SM might stop covering the
+  // loaded HBM latency (kernel 0.151 ms at 16 queries -> 0.174 at 128, proportional to the SM count).  L2
+  // prefetches need no shared-memory slot: request the next unit's tile one unit (~3 us) ahead.
+  // MEASURED AND REJECTED (profiles/r02_prefetch_ab.log): with the prefetch on, the 16-query scan slows from
+  // 0.151 to 0.211 ms and every other shape by 8-30 %: the extra requests compete with the ring's own loads
+  // instead of shortening them.  Off by default; the knob stays for A/B runs.
+  cfg.prefetch = getenv("MMRS_K2_PREFETCH") ? atoi(getenv("MMRS_K2_PREFETCH")) : 0;
   cfg.debug_skip_epilogue = getenv("MMRS_K2_DEBUG_SKIP_EPI") ? atoi(getenv("MMRS_K2_DEBUG_SKIP_EPI")) : 0;   // 1: no epilogue, 2: nothing passes
   // Up to 64 queries the CTA is sized so that TWO fit on an SM (<= 113 KB of shared memory, 80
   // registers x 384 threads, <= 256 TMEM columns each): the scans of two searches in flight on
@@ -601,22 +608,36 @@ cudaError_t launch_scan_mma(const ScanParams& p, const __nv_bfloat16* q_bf16, in
   };
   if (small) {
     switch (mode) {
-      case kModeScores: return go(scan_mma_kernel<kModeScores, 8, false>);
-      case kModeDense: return go(scan_mma_kernel<kModeDense, 8, false>);
-      default: return go(scan_mma_kernel<kModeFilter, 8, false>);
+      case kModeScores: return go(scan_mma_kernel<kModeScores, 8, false, 1>);
+      case kModeDense: return go(scan_mma_kernel<kModeDense, 8, false, 1>);
+      default: return go(scan_mma_kernel<kModeFilter, 8, false, 1>);
+    }
+  }
+  if (pair && split == 1) {
+    switch (mode) {   // > 64 queries: one CTA per SM, CTA pairs, 16 epilogue warps each
+      case kModeScores: return go(scan_mma_kernel<kModeScores, 16, true, 1>);
+      case kModeDense: return go(scan_mma_kernel<kModeDense, 16, true, 1>);
+      default: return go(scan_mma_kernel<kModeFilter, 16, true, 1>);
     }
   }
   if (pair) {
-    switch (mode) {   // > 64 queries: one CTA per SM, CTA pairs, 16 epilogue warps each
-      case kModeScores: return go(scan_mma_kernel<kModeScores, 16, true>);
-      case kModeDense: return go(scan_mma_kernel<kModeDense, 16, true>);
-      default: return go(scan_mma_kernel<kModeFilter, 16, true>);
+    switch (mode) {   // fp32 emulation, 49..128 queries: CTA pairs, three planes per operand
+      case kModeScores: return go(scan_mma_kernel<kModeScores, 16, true, 3>);
+      case kModeDense: return go(scan_mma_kernel<kModeDense, 16, true, 3>);
+      default: return go(scan_mma_kernel<kModeFilter, 16, true, 3>);
     }
   }
-  switch (mode) {   // fp32 emulation (three planes per operand) and MMRS_K2_NO_PAIR
-    case kModeScores: return go(scan_mma_kernel<kModeScores, 16, false>);
-    case kModeDense: return go(scan_mma_kernel<kModeDense, 16, false>);
-    default: return go(scan_mma_kernel<kModeFilter, 16, false>);
+  if (split == 3) {
+    switch (mode) {   // fp32 emulation, up to 48 queries
+      case kModeScores: return go(scan_mma_kernel<kModeScores, 16, false, 3>);
+      case kModeDense: return go(scan_mma_kernel<kModeDense, 16, false, 3>);
+      default: return go(scan_mma_kernel<kModeFilter, 16, false, 3>);
+    }
+  }
+  switch (mode) {   // MMRS_K2_NO_PAIR / MMRS_K2_BIG_SMEM
+    case kModeScores: return go(scan_mma_kernel<kModeScores, 16, false, 1>);
+    case kModeDense: return go(scan_mma_kernel<kModeDense, 16, false, 1>);
+    default: return go(scan_mma_kernel<kModeFilter, 16, false, 1>);
   }
 }
 
