@@ -28,7 +28,7 @@ def test_sharded_search_and_selfjoin_on_all_visible_gpus():
     world = 2 if n < 4 else (4 if n < 8 else 8)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), str(ROOT / "tools" / "multigpu_check.py")]
-    env = dict(os.environ, MMRS_GATHER_TIMEOUT_MS="60000")
+    env = dict(os.environ, MMRS_GATHER_TIMEOUT_MS="60000", OMP_NUM_THREADS="4")
     res = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
     tail = (res.stdout + res.stderr)[-3000:]
     assert res.returncode == 0, tail
