@@ -507,7 +507,7 @@ struct GraphKey {
 static uint64_t knob_hash() {
   static const char* const kNames[] = {"MMRS_K2_SMALL_MAX", "MMRS_K2_BIG_SMEM", "MMRS_K2_CTAS_PER_SM", "MMRS_K2_QCHUNKS",
                                        "MMRS_K2_NO_PAIR", "MMRS_K2_PAIR_MIN", "MMRS_K2_DEBUG_SKIP_EPI", "MMRS_NO_PDL",
-                                       "MMRS_K2_STICKY", "MMRS_K2_HBM_PAIRS", "MMRS_K2_PREFETCH"};
+                                       "MMRS_K2_STICKY", "MMRS_K2_HBM_PAIRS", "MMRS_K2_PREFETCH", "MMRS_K2_SMALL_PAIR_MAX"};
   uint64_t h = 1469598103934665603ull;
   for (const char* name : kNames) {
     const char* v = getenv(name);

@@ -48,7 +48,7 @@ constexpr int kABytes = kBlockM * kBlockK * 2;   // 16 KiB
 constexpr int kMaxStages = 8;
 constexpr uint32_t kStash = 4;            // parked candidates per epilogue thread before a flush
 
-template <int CHUNKS>   // query chunks whose thresholds a CTA keeps: 1, or kMaxQChunks in pair mode
+template <int CHUNKS, int EPI = kMaxEpiWarps>   // query chunks whose thresholds a CTA keeps (1, or kMaxQChunks in pair mode); epilogue warps
 struct MmaSharedT {
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
@@ -58,9 +58,8 @@ struct MmaSharedT {
   volatile uint32_t abort;
   alignas(16) float thr[kMaxQ * CHUNKS];       // exact bound on the scaled score
   alignas(16) float thr_raw[kMaxQ * CHUNKS];   // conservative bound on the RAW accumulator (thr / scale, nudged down)
-  alignas(16) uint2 stash[kMaxEpiWarps][kStash * 32];  // per epilogue thread: parked (column, score) pairs
+  alignas(16) uint2 stash[EPI][kStash * 32];  // per epilogue thread: parked (column, score) pairs
 };
-using MmaShared = MmaSharedT<1>;
 
 struct MmaCfg {
   int32_t n_umma;        // UMMA N: queries of this pass rounded up to 16
@@ -86,7 +85,8 @@ template <int MODE, int EPI_WARPS, bool PAIR, int SPLIT>
 __global__ void __launch_bounds__((kCtrlWarps + EPI_WARPS) * 32, EPI_WARPS == 8 ? 2 : 1)
 scan_mma_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_q,
                 const ScanParams p, const MmaCfg cfg, int32_t* flags) {
-  using Shared = MmaSharedT<PAIR ? kMaxQChunks : 1>;
+  // the two-per-SM variants (8 epilogue warps) scan ONE query chunk and keep the small layout
+  using Shared = MmaSharedT<(PAIR && EPI_WARPS == 16) ? kMaxQChunks : 1, EPI_WARPS>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic smem: [stages x (A 16 KiB | B rows*128 B)] then Shared; the ring must be
   // 1024-byte aligned for the 128-byte swizzle.  B rows: n_umma, in pair mode n_umma / 2.
@@ -539,13 +539,23 @@ cudaError_t launch_scan_mma(const ScanParams& p, const __nv_bfloat16* q_bf16, in
   int small_max = 64;   // 33..64 queries: 3-4 ring stages per CTA, two CTAs per SM
   if (const char* e = getenv("MMRS_K2_SMALL_MAX")) small_max = atoi(e);
   const bool small = split == 1 && cfg.n_umma <= small_max && getenv("MMRS_K2_BIG_SMEM") == nullptr;
+  // MEASURED AND REJECTED (profiles/r02_small_pair_ab.log): 65..128 queries as CTA pairs sized like the small
+  // variant ("small pair": 8 epilogue warps, <= 113 KB, 80 registers), so that a pair-mode scan does not own its
+  // SMs and the second search in flight runs beside it.  With four 24 KB stages the scan itself slows from 0.158 to
+  // 0.183 ms and the step from 0.215 to 0.293 ms at 128 queries (0.210 -> 0.255 at 96; no change at 64).  Off by
+  // default (MMRS_K2_SMALL_PAIR_MAX=128 turns it on for A/B runs).
+  int small_pair_max = 0;
+  if (const char* e = getenv("MMRS_K2_SMALL_PAIR_MAX")) small_pair_max = atoi(e);
+  const bool small_pair = !small && split == 1 && n_qchunks == 1 && cfg.n_umma <= small_pair_max &&
+                          getenv("MMRS_K2_BIG_SMEM") == nullptr && getenv("MMRS_K2_NO_PAIR") == nullptr;
   // Above that the kernel runs as CTA pairs (cta_group::2, see the file header)
   int pair_min = 64;
   if (const char* e = getenv("MMRS_K2_PAIR_MIN")) pair_min = atoi(e);
   // fp32 emulation: up to 48 queries a single CTA per SM holds three stages of all six planes; beyond that the
   // pair halves the query planes per CTA, so that 100 queries (BASELINE C1) are ONE pass over the gallery
   // planes instead of three (1.49 ms -> one 3 GB stream at 1M x 512, profiles/r02_fp32_bench_*.log)
-  const bool pair = !small && (split == 1 ? cfg.n_umma > pair_min : p.nq > kSplitMaxQ) && getenv("MMRS_K2_NO_PAIR") == nullptr;
+  const bool pair = small_pair ||
+                    (!small && (split == 1 ? cfg.n_umma > pair_min : p.nq > kSplitMaxQ) && getenv("MMRS_K2_NO_PAIR") == nullptr);
   if (pair) cfg.n_umma = (cfg.n_umma + 31) / 32 * 32;   // each CTA stages half the query rows
   int cols = 32;
   while (cols < 2 * cfg.n_umma) cols <<= 1;
@@ -553,8 +563,9 @@ cudaError_t launch_scan_mma(const ScanParams& p, const __nv_bfloat16* q_bf16, in
   cfg.acc_stride = cols / 2;
   const int b_rows = pair ? cfg.n_umma / 2 : cfg.n_umma;
   const size_t stage_bytes = split * (static_cast<size_t>(kABytes) + static_cast<size_t>(b_rows) * kBlockK * 2);
-  const size_t shared_struct = pair ? sizeof(MmaSharedT<kMaxQChunks>) : sizeof(MmaShared);
-  const size_t budget = (small ? 113 * 1024 : 227 * 1024) - shared_struct - 1024 - (small ? 1024 : 0);
+  const bool half_sm = small || small_pair;   // footprint of half an SM: two CTAs (of two searches) per SM
+  const size_t shared_struct = half_sm ? sizeof(MmaSharedT<1, 8>) : (pair ? sizeof(MmaSharedT<kMaxQChunks>) : sizeof(MmaSharedT<1>));
+  const size_t budget = (half_sm ? 113 * 1024 : 227 * 1024) - shared_struct - 1024 - (half_sm ? 1024 : 0);
   int stages = static_cast<int>(budget / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return cudaErrorInvalidValue;
@@ -603,7 +614,7 @@ cudaError_t launch_scan_mma(const ScanParams& p, const __nv_bfloat16* q_bf16, in
   auto go = [&](auto kernel) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    return launch_pdl_cluster(kernel, grid, dim3((kCtrlWarps + (small ? 8 : 16)) * 32), smem, stream, pair ? 2u : 1u,
+    return launch_pdl_cluster(kernel, grid, dim3((kCtrlWarps + (half_sm ? 8 : 16)) * 32), smem, stream, pair ? 2u : 1u,
                               map_g, map_q, p, cfg, flags);
   };
   if (small) {
@@ -613,8 +624,15 @@ cudaError_t launch_scan_mma(const ScanParams& p, const __nv_bfloat16* q_bf16, in
       default: return go(scan_mma_kernel<kModeFilter, 8, false, 1>);
     }
   }
+  if (small_pair) {
+    switch (mode) {   // 65..128 queries: CTA pairs with the footprint of half an SM
+      case kModeScores: return go(scan_mma_kernel<kModeScores, 8, true, 1>);
+      case kModeDense: return go(scan_mma_kernel<kModeDense, 8, true, 1>);
+      default: return go(scan_mma_kernel<kModeFilter, 8, true, 1>);
+    }
+  }
   if (pair && split == 1) {
-    switch (mode) {   // > 64 queries: one CTA per SM, CTA pairs, 16 epilogue warps each
+    switch (mode) {   // > 128 queries: one CTA per SM, CTA pairs, 16 epilogue warps each
       case kModeScores: return go(scan_mma_kernel<kModeScores, 16, true, 1>);
       case kModeDense: return go(scan_mma_kernel<kModeDense, 16, true, 1>);
       default: return go(scan_mma_kernel<kModeFilter, 16, true, 1>);
