@@ -353,3 +353,38 @@ def test_upload_cache_is_keyed_on_identity_not_address(mm, monkeypatch):
     assert len(made) == 5                                          # numpy inputs are never cached
     S._last_upload.clear()
     del ptr, g3
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): one JSON line with the contract's keys,
+    the same workload description as our arm, honouring --steps / --warmup, no GPU needed."""
+    import json
+    import sys
+    root = Path(__file__).resolve().parent.parent
+    out = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--rows", "30000", "--dim", "64",
+                          "--batch", "4", "--k", "5", "--steps", "3", "--warmup", "2", "--gpus", "1"],
+                         capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "top-k queries/sec" and d["unit"] == "queries/s"
+    assert d["steps"] == 3 and d["warmup"] == 2 and d["n_gpus"] == 1 and d["higher_is_better"] is True
+    assert d["scaling"] == "strong" and d["vs_baseline"] is None and d["value"] > 0
+    assert d["config"]["global_rows"] == 30000 and d["config"]["queries_per_step"] == 4 and d["config"]["k"] == 5
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # ranks other than 0 print nothing and exit 0 (torchrun launches the arm on every rank)
+    out = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--gpus", "2"],
+                         capture_output=True, text=True, timeout=120, cwd=root, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
+    assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_bench_traffic_table_is_keyed_by_shape():
+    import json
+    root = Path(__file__).resolve().parent.parent
+    table = json.loads((root / "profiles" / "traffic.json").read_text())
+    keys = [k for k in table if not k.startswith("_")]
+    assert keys and all("@" in k and "x" in k.split("@")[1] and "q" in k.split("@")[1] for k in keys)
+    for k in keys:
+        assert table[k]["dram_bytes_read"] > 0 and (root / table[k]["source"].split(" ")[0]).exists(), k
