@@ -546,6 +546,26 @@ class Bench:
                                    "(two searches in flight can share gallery reads through L2, so > 1 is possible)")
             out[f"1Mx{dim}"] = entry
             del gal
+        # unit-gaussian rows are the best case for nobody in particular, but show it -- a
+        # clustered gallery (1000 centroids + noise, queries drawn near centroids, stored cluster by cluster).
+        # The thresholds come from a strided SAMPLE's order statistics, which are distribution-free, so the
+        # appends per phase (k x ratio) and hence the step time should not move.
+        gen = torch.Generator(device=self.device).manual_seed(7)
+        cent = torch.randn((1000, 768), generator=gen, device=self.device)
+        lab = torch.arange(1000, device=self.device).repeat_interleave(1000)
+        g = torch.empty((1_000_000, 768), dtype=torch.bfloat16, device=self.device)
+        for lo in range(0, 1_000_000, 1 << 18):
+            x = cent[lab[lo:lo + (1 << 18)]] + 0.5 * torch.randn((min(1 << 18, 1_000_000 - lo), 768), generator=gen, device=self.device)
+            g[lo:lo + (1 << 18)] = (x / x.norm(dim=-1, keepdim=True)).to(torch.bfloat16)
+        gal = mm.DeviceGallery(g)
+        q = (cent[torch.arange(0, 1000, 63, device=self.device)[:Q_STEP]] +
+             0.3 * torch.randn((Q_STEP, 768), generator=gen, device=self.device)).cpu().pin_memory()
+        r = self.measure(gal, None, q, TOPK, steps=200, warmup=10, e2e=False)
+        out["1Mx768_clustered"] = {"workload": "1M x 768 bf16 gallery, 1000 clusters stored cluster by cluster, 16 queries near centroids, top-100",
+                                   "value": r["value"], "unit": "queries/s", "ms_per_step": r["ms_per_step"], "roofline": r["roofline"],
+                                   "blocking_call_ms": r["blocking_call_ms"],
+                                   "parity_check": self.parity(gal, None, g, q, TOPK, r["out"])}
+        del gal, g
         return out
 
     def leg_c5(self, gal, sg):
