@@ -65,6 +65,7 @@ def parse():
                     help="comma list of extra legs: gallery_1m,c5,c3,parity  ('all', 'none')")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--one-stream", action="store_true", help="keep the batches in flight on ONE stream")
+    ap.add_argument("--no-fused", action="store_true", help="N > 1: NCCL all-gather variant instead of the fused NVLink gather")
     ap.add_argument("--c3-rows", type=int, default=C3_ROWS)
     ap.add_argument("--c5-queries", type=int, default=C5_QUERIES)
     return ap.parse_args()
@@ -660,11 +661,13 @@ def main():
     lo, hi = shard_bounds(args.rows, world)[rank]
     shard = device_gallery_shard(torch, hi - lo, args.dim, seed=0, shard_id=rank * 64 + world, device=b.device)
     gal = mm.DeviceGallery(shard, row_offset=lo)
-    sg = mm.ShardedGallery(gal, args.rows) if world > 1 else None
+    sg = mm.ShardedGallery(gal, args.rows, fused=False if args.no_fused else None) if world > 1 else None
     q_host = torch.randn((args.batch, args.dim), generator=torch.Generator().manual_seed(1)).pin_memory()
     t_setup = time.perf_counter() - b.t_start
 
     head = b.measure(gal, sg, q_host, args.k, args.steps, args.warmup)
+    gather_desc = None if sg is None else ("fused into the select kernels over NVLink peer memory" if sg.fused_active
+                                           else "NCCL all_gather_into_tensor of packed keys + merge kernel")
     extra = {}
 
     def run_leg(name, fn):
@@ -703,6 +706,7 @@ def main():
             "config": workload_config(args, world), "clocks": head["clocks"], "e2e": head["e2e"],
             "gpu_launches": head["launches"], "roofline": head["roofline"], "cpu_baseline": cpu,
             "pipelining": f"{b.DEPTH} batches in flight" + ("" if args.one_stream else f" on {b.DEPTH} streams"),
+            "gather": gather_desc,
             "blocking_call_ms": head.get("blocking_call_ms"),
             # one gallery pass per step / step time / (N x measured copy peak); see roofline.whole_step_note
             "aggregate_hbm_frac": (args.rows * args.dim * 2) / (head["ms_per_step"] / 1e3) / 1e9 / (world * b.peaks["hbm"]),

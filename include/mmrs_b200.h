@@ -229,7 +229,9 @@ int mmrs_topk_merge_keys_async(const uint64_t* d_keys_in, int32_t n_lists, int32
  * h_status: pinned int32 [world + 2]; after the stream has completed,
  * mmrs_gather_status(h_status, world) is the outcome on every rank alike (MMRS_ERR_RETRY when any
  * rank overflowed; MMRS_ERR_TIMEOUT when a peer never arrived).  n_queries <= 1024, world <= 64,
- * k_local must be the same on every rank.
+ * k_local must be the same on every rank and every shard must hold at least k_local rows -- a rank that
+ * contributes fewer keys than min(k_out, its rows) can drop rows of the global top-k; callers with shorter
+ * shards use the keys variant below and pad.
  */
 int mmrs_search_topk_fused_gather_async(
     const void* d_gallery, int64_t n_rows, int32_t dim, int64_t ld_gallery, int32_t gallery_dtype,

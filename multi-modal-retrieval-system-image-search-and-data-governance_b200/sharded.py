@@ -115,9 +115,10 @@ class ShardedGallery:
             from .search import search_topk as local_search
         self._search = local_search
         self._merge = merge or _merge_cuda
-        # the shortest shard decides how many keys every rank contributes per query: ONE k_local for all
-        # ranks (buffer strides and the merge shape must agree); shards shorter than k use the padded
-        # NCCL variant.  One small collective at construction.
+        # The fused gather needs every rank to contribute exactly k keys per query (one buffer stride and one
+        # merge shape for all ranks; a rank that contributed fewer than min(k, its rows) could drop rows of the
+        # global top-k), so it is used only when the SHORTEST shard has at least k rows; otherwise the NCCL
+        # variant pads short lists with key 0.  One small collective at construction.
         self.min_shard_rows = len(local)
         if self.world > 1:
             sizes = [None] * self.world
@@ -288,7 +289,7 @@ class ShardedGallery:
             torch.cuda.set_device(dev)
         stream = torch.cuda.current_stream(dev)
         nq = int(queries.shape[0])
-        k_local = min(k, self.min_shard_rows)            # the same on every rank
+        k_local = k                                      # every shard has >= k rows (checked by search_topk)
         slot = gal.search_slot(nq, k_local, False, stream.cuda_stream)
         st = self._fused_state(slot, nq, k_local)         # collective on first use of the slot
         q, on_host, keep = self._stage_queries(slot, queries)
@@ -340,8 +341,8 @@ class ShardedGallery:
             if nq == 0:
                 out_t = self.search_topk_general(queries, k, normalize_queries=normalize_queries, scale=scale, path=path)
                 return out_t if sync else _PendingSharded(lambda: out_t, None)
-            # fused NVLink gather: every rank must be able to contribute k_local keys with world * k_local >= k
-            fused = (self._fused_ok and 1 <= nq <= 1024 and self.world * min(k, self.min_shard_rows) >= k)
+            # fused NVLink gather: every rank contributes its full top-k (needs >= k rows in every shard)
+            fused = self._fused_ok and 1 <= nq <= 1024 and self.min_shard_rows >= k
             finish = None
             if fused:
                 try:

@@ -79,11 +79,14 @@ for t in (0, 5):
     near_equal(outs[t][1], outs[t][0], wi, wv, 40)
 torch.cuda.synchronize()
 
-# a short last shard: one k_local for all ranks (fused), and shards too short for it (NCCL variant, padded)
-for n_short, want_fused in ((128 * (world - 1) + 50, world * 50 >= k), (128 * (world - 1) + 10, world * 10 >= k)):
+# unequal shards: the last one just long enough for k (fused), and too short for it (NCCL variant, lists padded
+# with key 0) -- in the second case most of the global top-k comes from the long shards, so a rank that
+# contributed fewer than min(k, its rows) keys would be caught here
+for last_rows, want_fused in ((110, True), (50, False), (10, False)):
+    n_short = 128 * (world - 1) + last_rows
     gs = oracle.synthetic_gallery(n_short, 64, seed=7, dtype=torch.bfloat16)
     sgs = mmrs_b200.ShardedGallery.from_full(gs, device=dev)
-    assert sgs.min_shard_rows == n_short - 128 * (world - 1)
+    assert sgs.min_shard_rows == last_rows
     qq = oracle.synthetic_queries(4, 64, seed=3)
     v, i = sgs.search_topk(qq.to(dev), k)
     wv, wi = oracle.search_topk(qq, gs, k, mode="bf16")
