@@ -13,7 +13,7 @@ for l in sys.stdin:
         print('    ', [(t['kernel'], round(t['ms']*1000,1)) for t in d.get('kernel_timeline_ms', [])][-5:])
 "; }
 P=29700
-for rep in 1 2; do
+for rep in $(seq 1 ${REPS:-2}); do
   for F in "" "--no-fused"; do
     P=$((P+1)); run $P --rows $((N*1000000)) --dim 512 --batch 16 --steps 300 --warmup 10 --no-cpu --legs parity $F
     P=$((P+1)); run $P --rows $((N*1000000)) --dim 512 --batch 128 --steps 300 --warmup 10 --no-cpu --legs none $F
