@@ -40,6 +40,10 @@ def _worker(rank, world, port, n_rows, k, out_dir):
 
     sg = mmrs_b200.ShardedGallery(_HostShard(g[lo:hi], lo), n_rows, local_search=local_search,
                                   merge=oracle.merge_topk)
+    # the shortest shard is known on every rank (it decides whether the fused NVLink gather may be used:
+    # only when every shard can contribute its full top-k)
+    assert sg.min_shard_rows == min(b - a for a, b in mmrs_b200.shard_bounds(n_rows, world))
+    assert not sg.fused_active
     v, i = sg.search_topk(q, k)
     want_v, want_i = oracle.search_topk(q, g, k)
     assert torch.equal(i, want_i), (rank, i, want_i)
