@@ -388,3 +388,17 @@ def test_bench_traffic_table_is_keyed_by_shape():
     assert keys and all("@" in k and "x" in k.split("@")[1] and "q" in k.split("@")[1] for k in keys)
     for k in keys:
         assert table[k]["dram_bytes_read"] > 0 and (root / table[k]["source"].split(" ")[0]).exists(), k
+
+
+def test_calculate_image_hash_matches_reference(mm, tmp_path):
+    """calculate_image_hash (the exact predicate that confirms deletions) against the MD5s recorded from the
+    reference's tool/find_repeated.py:6-19 on the same generated image set; unreadable file -> None."""
+    import json
+    from conftest import GOLDEN
+    from golden_inputs import dedup_image_set
+    gold = json.loads((GOLDEN / "find_repeated_golden.json").read_text())
+    dedup_image_set(str(tmp_path))
+    got = {os.path.relpath(p, tmp_path): mm.calculate_image_hash(p) for p in sorted(mm.get_all_images(str(tmp_path)))}
+    assert got == gold["hashes"]
+    assert got["delete/broken.png"] is None
+    assert got["reference/sub/c.png"] == got["reference/sub/c_again.png"] == got["delete/nested/c_copy.png"]
